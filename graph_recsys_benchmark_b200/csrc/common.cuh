@@ -1,0 +1,52 @@
+// Shared helpers for libpeagnn_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/peagnn.h"
+
+namespace peagnn {
+
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return PEAGNN_ERR_CUDA;
+  }
+  return PEAGNN_OK;
+}
+
+#define PEAGNN_REQUIRE(cond, ...)        \
+  do {                                   \
+    if (!(cond)) {                       \
+      peagnn::set_error(__VA_ARGS__);    \
+      return PEAGNN_ERR_ARG;             \
+    }                                    \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kNumSMs = 148;  // B200
+
+__host__ __device__ __forceinline__ int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
+__host__ __device__ __forceinline__ int64_t imax64(int64_t a, int64_t b) { return a > b ? a : b; }
+
+__device__ __forceinline__ float4 ldg4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float leaky(float s, float slope) { return s > 0.f ? s : slope * s; }
+
+// -log(sigmoid(z)) evaluated the way the reference does it (sigmoid().log(), models/base.py:48):
+// no logsigmoid stabilisation, so a very negative z overflows to +inf exactly as upstream.
+__device__ __forceinline__ float neg_log_sigmoid_ref(float z) {
+  float s = 1.f / (1.f + expf(-z));
+  return -logf(s);
+}
+
+}  // namespace peagnn

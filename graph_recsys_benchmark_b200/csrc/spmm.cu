@@ -1,0 +1,128 @@
+// K1 / K2: weighted CSR aggregation - the message passing of GCNConv and SAGEConv
+// (reference call sites models/peagcn.py:16-21, models/peasage.py:16-21 via models/base.py:137-139;
+// PyG-1.5.0 gather -> scale -> torch_scatter.scatter_add restated as a gather-side segmented sum).
+#include "csr_traverse.cuh"
+
+namespace peagnn {
+
+template <int CPL, int G>
+struct SpmmOp {
+  static constexpr int NV = 4 * CPL;
+  static constexpr bool kMax = false;
+  static constexpr bool kUseW2 = false;
+  int heads;
+  const float* __restrict__ X;
+  int64_t ldx;
+  int f4;  // float4 chunks per row
+  float* __restrict__ out;
+  int64_t ldo;
+  const float* __restrict__ rs;
+  const float* __restrict__ cs;
+  const float* __restrict__ bias;
+  int row_offset;
+  int self_loop, relu, accumulate;
+
+  __device__ __forceinline__ void row_begin(int, int, int, unsigned) {}
+
+  __device__ __forceinline__ Edge load_edge(int, int c) const {
+    Edge e;
+    e.c = c;
+    e.w = cs ? __ldg(cs + c) : 1.f;
+    e.w2 = 0.f;
+    return e;
+  }
+
+  __device__ __forceinline__ void apply(float* acc, int, int c, float w, float, int gl, unsigned) const {
+    const float* xr = X + (int64_t)c * ldx;
+#pragma unroll
+    for (int ch = 0; ch < CPL; ++ch) {
+      const int idx = gl + ch * G;
+      if (idx < f4) {
+        const float4 v = ldg4(xr + 4 * idx);
+        acc[4 * ch + 0] = fmaf(w, v.x, acc[4 * ch + 0]);
+        acc[4 * ch + 1] = fmaf(w, v.y, acc[4 * ch + 1]);
+        acc[4 * ch + 2] = fmaf(w, v.z, acc[4 * ch + 2]);
+        acc[4 * ch + 3] = fmaf(w, v.w, acc[4 * ch + 3]);
+      }
+    }
+  }
+
+  __device__ __forceinline__ void finish(float* acc, int i, int, int gl, unsigned) const {
+    const int gi = row_offset + i;
+    const float r = rs ? __ldg(rs + gi) : 1.f;
+    const float sw = self_loop ? (cs ? __ldg(cs + gi) : 1.f) : 0.f;
+    const float* xi = X + (int64_t)gi * ldx;
+    float* o = out + (int64_t)i * ldo;
+#pragma unroll
+    for (int ch = 0; ch < CPL; ++ch) {
+      const int idx = gl + ch * G;
+      if (idx < f4) {
+        float4 a = make_float4(acc[4 * ch], acc[4 * ch + 1], acc[4 * ch + 2], acc[4 * ch + 3]);
+        if (self_loop) {
+          const float4 v = ldg4(xi + 4 * idx);
+          a.x = fmaf(sw, v.x, a.x);
+          a.y = fmaf(sw, v.y, a.y);
+          a.z = fmaf(sw, v.z, a.z);
+          a.w = fmaf(sw, v.w, a.w);
+        }
+        a.x *= r; a.y *= r; a.z *= r; a.w *= r;
+        if (bias) {
+          const float4 b = ldg4(bias + 4 * idx);
+          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        if (relu) {
+          a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+        }
+        if (accumulate) {
+          const float4 p = *reinterpret_cast<const float4*>(o + 4 * idx);
+          a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+        }
+        st4(o + 4 * idx, a);
+      }
+    }
+  }
+};
+
+template <int CPL, int G, int IPL>
+static int run_spmm(const peagnn_csr_t& g, const float* X, int64_t ldx, int feat, float* out,
+                    int64_t ldo, const float* rs, const float* cs, int self_loop, const float* bias,
+                    int relu, int accumulate, cudaStream_t stream) {
+  SpmmOp<CPL, G> op;
+  op.heads = 1;
+  op.X = X; op.ldx = ldx; op.f4 = feat / 4; op.out = out; op.ldo = ldo;
+  op.rs = rs; op.cs = cs; op.bias = bias; op.row_offset = g.row_offset;
+  op.self_loop = self_loop; op.relu = relu; op.accumulate = accumulate;
+  return launch_csr<SpmmOp<CPL, G>, G, IPL>(g, op, stream, "peagnn_spmm");
+}
+
+}  // namespace peagnn
+
+using namespace peagnn;
+
+extern "C" size_t peagnn_partial_floats(int32_t n_chunks, int32_t feat, int32_t heads) {
+  const Geometry ge = geometry_for(feat);
+  return (size_t)(n_chunks > 0 ? n_chunks : 0) * (size_t)(heads > 0 ? heads : 1) * (size_t)ge.G *
+         (size_t)(4 * ge.CPL + 2);
+}
+
+extern "C" int peagnn_spmm(const peagnn_csr_t* g, const float* X, int64_t ldx, int32_t feat,
+                           float* out, int64_t ldo, const float* rs, const float* cs,
+                           int self_loop, const float* bias, int relu, int accumulate,
+                           peagnn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PEAGNN_REQUIRE(g && g->rowptr && (g->col || g->nrows == 0), "peagnn_spmm: null graph");
+  PEAGNN_REQUIRE(feat > 0 && feat % 4 == 0 && feat <= 512, "peagnn_spmm: feat=%d must be a multiple of 4, <= 512", feat);
+  PEAGNN_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0 && ldx >= feat && ldo >= feat, "peagnn_spmm: leading dims must be multiples of 4 and >= feat");
+  PEAGNN_REQUIRE(aligned16(X) && aligned16(out) && (!bias || aligned16(bias)), "peagnn_spmm: pointers must be 16-byte aligned");
+  if (g->nrows == 0) return PEAGNN_OK;
+  const Geometry ge = geometry_for(feat);
+#define PEAGNN_SPMM_CASE(CPL_, G_, IPL_) \
+  return run_spmm<CPL_, G_, IPL_>(*g, X, ldx, feat, out, ldo, rs, cs, self_loop, bias, relu, accumulate, stream)
+  if (ge.G == 4) PEAGNN_SPMM_CASE(1, 4, 2);
+  if (ge.G == 8) PEAGNN_SPMM_CASE(1, 8, 1);
+  if (ge.G == 16) PEAGNN_SPMM_CASE(1, 16, 1);
+  if (ge.CPL == 1) PEAGNN_SPMM_CASE(1, 32, 1);
+  if (ge.CPL == 2) PEAGNN_SPMM_CASE(2, 32, 1);
+  PEAGNN_SPMM_CASE(4, 32, 1);
+#undef PEAGNN_SPMM_CASE
+}

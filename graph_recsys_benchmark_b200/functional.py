@@ -1,0 +1,463 @@
+"""Autograd bindings of the C-ABI kernels (``include/peagnn.h``).
+
+Each ``torch.autograd.Function`` below is a thin shim: validate on the Python side (dtype,
+device, contiguity - the reference raises Python exceptions), hand raw device
+pointers to ``libpeagnn_sm100.so`` on the current stream, keep what backward needs.  No tensor
+math happens in torch on these paths; there is no CPU path at all.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .graph import _ptr, _stream
+
+NEG_SLOPE = 0.2
+
+
+def _req(t, name, dim=2):
+    if not t.is_cuda:
+        raise RuntimeError('%s must live on a CUDA device (no CPU path in this package)' % name)
+    if t.dtype != torch.float32:
+        raise TypeError('%s must be float32, got %s' % (name, t.dtype))
+    if t.dim() != dim:
+        raise ValueError('%s must be %d-d' % (name, dim))
+    return t
+
+
+def _rows(t):
+    """Row-major 2-d view with a unit inner stride and a 4-element aligned leading dimension."""
+    if t.stride(1) != 1 or t.stride(0) % 4 != 0 or t.stride(0) < t.shape[1] or t.data_ptr() % 16 != 0:
+        t = t.contiguous()
+    return t
+
+
+def _ws(n, device):
+    return torch.empty(max(int(n), 1), dtype=torch.float32, device=device)
+
+
+# ---------------------------------------------------------------------------------------------
+# raw launches
+# ---------------------------------------------------------------------------------------------
+def spmm_raw(csr, X, feat, out, rs=None, cs=None, self_loop=False, bias=None, relu=False, accumulate=False):
+    view = csr.view(feat)
+    with torch.cuda.device(X.device):
+        _lib.call('peagnn_spmm', C.byref(view), _ptr(X), X.stride(0), feat, _ptr(out), out.stride(0),
+                  _ptr(rs), _ptr(cs), int(self_loop), _ptr(bias), int(relu), int(accumulate), _stream())
+    return out
+
+
+def linear_raw(X, W, out, w_is_out_in, bias=None, relu=False, accumulate=False, mask=None):
+    n, K = X.shape
+    M = out.shape[1]
+    with torch.cuda.device(X.device):
+        _lib.call('peagnn_linear', _ptr(X), X.stride(0), _ptr(mask), mask.stride(0) if mask is not None else 0,
+                  n, K, M, _ptr(W), int(w_is_out_in), _ptr(bias), int(relu), int(accumulate),
+                  _ptr(out), out.stride(0), _stream())
+    return out
+
+
+def wgrad_raw(X, dY, K, M, w_is_out_in, dW, db, mask=None):
+    n = dY.shape[0]
+    need = int(_lib.query('peagnn_wgrad_workspace_floats', n, K, M))
+    ws = _ws(need, dY.device)
+    with torch.cuda.device(dY.device):
+        _lib.call('peagnn_linear_wgrad', _ptr(X), X.stride(0) if X is not None else 0, _ptr(dY), dY.stride(0),
+                  _ptr(mask), mask.stride(0) if mask is not None else 0, n, K, M, int(w_is_out_in),
+                  _ptr(dW), _ptr(db), _ptr(ws), need, _stream())
+
+
+def relu_backward_raw(dy, act):
+    out = torch.empty_like(act)
+    with torch.cuda.device(dy.device):
+        _lib.call('peagnn_relu_backward', _ptr(dy), dy.stride(0), _ptr(act), act.stride(0), dy.shape[0],
+                  dy.shape[1], _ptr(out), out.stride(0), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# K1/K2  aggregation
+# ---------------------------------------------------------------------------------------------
+class _Aggregate(torch.autograd.Function):
+    """out = rs * (A (cs * X) [+ cs_i X_i]) [+ bias] [relu]   over graph.fwd; backward over graph.bwd
+    with rs / cs swapped (the transpose of diag(rs) A diag(cs) is diag(cs) A^T diag(rs))."""
+
+    @staticmethod
+    def forward(ctx, X, bias, graph, rs, cs, self_loop, relu):
+        X = _rows(_req(X, 'x'))
+        feat = X.shape[1]
+        out = torch.empty(graph.num_nodes, feat, dtype=torch.float32, device=X.device)
+        spmm_raw(graph.fwd, X, feat, out, rs, cs, self_loop, bias, relu)
+        ctx.graph, ctx.rs, ctx.cs, ctx.self_loop, ctx.relu = graph, rs, cs, self_loop, relu
+        ctx.has_bias = bias is not None
+        if relu:
+            ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _rows(dout)
+        if ctx.relu:
+            (out,) = ctx.saved_tensors
+            dout = relu_backward_raw(dout, out)
+        feat = dout.shape[1]
+        dX = db = None
+        if ctx.needs_input_grad[0]:
+            dX = torch.empty_like(dout)
+            spmm_raw(ctx.graph.bwd, dout, feat, dX, ctx.cs, ctx.rs, ctx.self_loop)
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            db = torch.empty(feat, dtype=torch.float32, device=dout.device)
+            wgrad_raw(None, dout, 0, feat, 0, None, db)
+        return dX, db, None, None, None, None, None
+
+
+def gcn_aggregate(X, graph, bias=None, relu=False):
+    """D^-1/2 (A + I) D^-1/2 X (+ bias)(relu)  with PyG-1.5.0's source-side degree."""
+    dis = graph.gcn_dis
+    return _Aggregate.apply(X, bias, graph, dis, dis, True, relu)
+
+
+def sage_mean_aggregate(X, graph, bias=None):
+    """mean_{j -> i} X_j (+ bias)  (0 for rows without in-edges; no self loops)."""
+    return _Aggregate.apply(X, bias, graph, graph.inv_in_degree, None, False, False)
+
+
+# ---------------------------------------------------------------------------------------------
+# K4  projections
+# ---------------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    """Y = act(X @ W (+ b)) with W either [in, out] (GCNConv.weight) or [out, in] (nn.Linear)."""
+
+    @staticmethod
+    def forward(ctx, X, W, bias, w_is_out_in, relu):
+        X = _rows(_req(X, 'x'))
+        W = _req(W, 'weight').contiguous()
+        K = X.shape[1]
+        M = W.shape[0] if w_is_out_in else W.shape[1]
+        if (W.shape[1] if w_is_out_in else W.shape[0]) != K:
+            raise ValueError('weight shape %s does not match input width %d' % (tuple(W.shape), K))
+        Y = torch.empty(X.shape[0], M, dtype=torch.float32, device=X.device)
+        linear_raw(X, W, Y, w_is_out_in, bias, relu)
+        ctx.w_is_out_in, ctx.relu, ctx.has_bias = w_is_out_in, relu, bias is not None
+        ctx.save_for_backward(X, W, Y if relu else None)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        X, W, Y = ctx.saved_tensors
+        dY = _rows(dY)
+        K, M = X.shape[1], dY.shape[1]
+        dX = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dX = torch.empty_like(X)
+            # dX = gate(dY) @ W^T : same kernel with the opposite weight layout
+            linear_raw(dY, W, dX, not ctx.w_is_out_in, None, False, False, mask=Y)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dW = torch.empty_like(W)
+            db = torch.empty(M, dtype=torch.float32, device=dY.device) if ctx.has_bias else None
+            wgrad_raw(X, dY, K, M, ctx.w_is_out_in, dW, db, mask=Y)
+        return dX, dW, db, None, None
+
+
+def linear(X, W, bias=None, w_is_out_in=True, relu=False):
+    return _Linear.apply(X, W, bias, w_is_out_in, relu)
+
+
+class _LinearAccumulate(torch.autograd.Function):
+    """Y = act(base + X @ W^T), W [out, in]; written in place over ``base`` (SAGEConv's
+    ``lin_rel(mean) + lin_root(x)``: the second projection accumulates onto the first)."""
+
+    @staticmethod
+    def forward(ctx, X, W, base, relu):
+        X = _rows(_req(X, 'x'))
+        W = _req(W, 'weight').contiguous()
+        if not base.is_contiguous():
+            raise ValueError('accumulation target must be contiguous')
+        linear_raw(X, W, base, True, None, relu, True)
+        ctx.mark_dirty(base)
+        ctx.relu = relu
+        ctx.save_for_backward(X, W, base if relu else None)
+        return base
+
+    @staticmethod
+    def backward(ctx, dY):
+        X, W, Y = ctx.saved_tensors
+        dY = _rows(dY)
+        if ctx.relu:
+            dY = relu_backward_raw(dY, Y)
+        K, M = X.shape[1], dY.shape[1]
+        dX = dW = None
+        if ctx.needs_input_grad[0]:
+            dX = torch.empty_like(X)
+            linear_raw(dY, W, dX, False)
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty_like(W)
+            wgrad_raw(X, dY, K, M, True, dW, None)
+        return dX, dW, dY, None
+
+
+def linear_accumulate(X, W, base, relu=False):
+    return _LinearAccumulate.apply(X, W, base, relu)
+
+
+# ---------------------------------------------------------------------------------------------
+# K3  GAT
+# ---------------------------------------------------------------------------------------------
+class _GatScores(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, H, att_i, att_j, heads):
+        H = _rows(_req(H, 'h'))
+        n = H.shape[0]
+        feat = H.shape[1] // heads
+        ai = torch.empty(n, heads, dtype=torch.float32, device=H.device)
+        aj = torch.empty_like(ai)
+        att_i, att_j = att_i.contiguous(), att_j.contiguous()
+        with torch.cuda.device(H.device):
+            _lib.call('peagnn_gat_scores', _ptr(H), H.stride(0), n, feat, heads, _ptr(att_i), _ptr(att_j),
+                      _ptr(ai), _ptr(aj), _stream())
+        ctx.heads = heads
+        ctx.save_for_backward(H, att_i, att_j)
+        return ai, aj
+
+    @staticmethod
+    def backward(ctx, d_ai, d_aj):
+        H, att_i, att_j = ctx.saved_tensors
+        heads = ctx.heads
+        n = H.shape[0]
+        feat = H.shape[1] // heads
+        d_ai, d_aj = d_ai.contiguous(), d_aj.contiguous()
+        dH = torch.empty_like(H)
+        d_att_i, d_att_j = torch.empty_like(att_i), torch.empty_like(att_j)
+        need = int(_lib.query('peagnn_wgrad_workspace_floats', n, heads * feat, 4))
+        ws = _ws(need, H.device)
+        with torch.cuda.device(H.device):
+            _lib.call('peagnn_gat_scores_backward', _ptr(H), H.stride(0), n, feat, heads, _ptr(att_i), _ptr(att_j),
+                      _ptr(d_ai), _ptr(d_aj), _ptr(dH), dH.stride(0), 0, _ptr(d_att_i), _ptr(d_att_j),
+                      _ptr(ws), need, _stream())
+        return dH, d_att_i, d_att_j, None
+
+
+class _GatAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, H, ai, aj, bias, graph, heads, relu):
+        H = _rows(_req(H, 'h'))
+        n = graph.num_nodes
+        feat = H.shape[1] // heads
+        dev = H.device
+        ai, aj = ai.contiguous(), aj.contiguous()
+        rowmax = torch.empty(n, heads, dtype=torch.float32, device=dev)
+        denom = torch.empty_like(rowmax)
+        out = torch.empty(n, heads * feat, dtype=torch.float32, device=dev)
+        view = graph.fwd.view(feat, heads)
+        with torch.cuda.device(dev):
+            _lib.call('peagnn_gat_rowmax', C.byref(view), _ptr(ai), _ptr(aj), heads, NEG_SLOPE, _ptr(rowmax), _stream())
+            _lib.call('peagnn_gat_aggregate', C.byref(view), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
+                      NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), int(relu), _stream())
+        ctx.graph, ctx.heads, ctx.relu, ctx.has_bias = graph, heads, relu, bias is not None
+        ctx.save_for_backward(H, ai, aj, rowmax, denom, out, bias)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        H, ai, aj, rowmax, denom, out, bias = ctx.saved_tensors
+        graph, heads = ctx.graph, ctx.heads
+        n = graph.num_nodes
+        feat = H.shape[1] // heads
+        dev = H.device
+        dout = _rows(dout)
+        if ctx.relu:
+            dout = relu_backward_raw(dout, out)
+        # the kernel needs <dout, aggregate-before-bias>; it subtracts the bias itself, and where a
+        # relu clamped the output dout is already 0, so passing the forward output is exact.
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            db = torch.empty(heads * feat, dtype=torch.float32, device=dev)
+            wgrad_raw(None, dout, 0, heads * feat, 0, None, db)
+        nnz = graph.fwd.nnz
+        alpha_e = torch.empty(max(nnz, 1), heads, dtype=torch.float32, device=dev)
+        ds_e = torch.empty_like(alpha_e)
+        alpha_s = torch.empty(n, heads, dtype=torch.float32, device=dev)
+        ds_s = torch.empty_like(alpha_s)
+        d_ai = torch.empty_like(alpha_s)
+        d_aj = torch.empty_like(alpha_s)
+        dH = torch.empty_like(H)
+        vf = graph.fwd.view(feat, heads)
+        vb = graph.bwd.view(feat, heads)
+        perm = graph.bwd_to_fwd
+        with torch.cuda.device(dev):
+            _lib.call('peagnn_gat_backward_dst', C.byref(vf), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
+                      NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), _ptr(dout), dout.stride(0),
+                      _ptr(alpha_e), _ptr(ds_e), _ptr(alpha_s), _ptr(ds_s), _ptr(d_ai), _stream())
+            _lib.call('peagnn_gat_backward_src', C.byref(vb), _ptr(perm), _ptr(alpha_e), _ptr(ds_e), _ptr(alpha_s),
+                      _ptr(ds_s), _ptr(dout), dout.stride(0), feat, heads, _ptr(dH), dH.stride(0), _ptr(d_aj),
+                      _stream())
+        return dH, d_ai, d_aj, db, None, None, None
+
+
+def gat_scores(H, att_i, att_j, heads):
+    return _GatScores.apply(H, att_i, att_j, heads)
+
+
+def gat_aggregate(H, ai, aj, graph, heads, bias=None, relu=False):
+    return _GatAggregate.apply(H, ai, aj, bias, graph, heads, relu)
+
+
+# ---------------------------------------------------------------------------------------------
+# K5  fusion across metapaths
+# ---------------------------------------------------------------------------------------------
+class _Fuse(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Z, att, mode, skip):
+        # Z: [N, P, D] contiguous
+        Z = _req(Z, 'channel outputs', 3).contiguous()
+        n, P, D = Z.shape
+        out = torch.empty(n, D, dtype=torch.float32, device=Z.device)
+        att2 = att.reshape(P, D).contiguous() if att is not None else None
+        with torch.cuda.device(Z.device):
+            _lib.call('peagnn_fuse_forward', _ptr(Z), P * D, n, P, D, _ptr(att2), mode, skip, _ptr(out), D, _stream())
+        ctx.mode, ctx.skip = mode, skip
+        ctx.att_shape = att.shape if att is not None else None
+        ctx.save_for_backward(Z, att2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        Z, att2 = ctx.saved_tensors
+        if ctx.skip >= 0:
+            raise RuntimeError('metapath ablation (metapath_idx) is an evaluation-only path (models/base.py:88-96)')
+        n, P, D = Z.shape
+        dout = _rows(dout)
+        dZ = torch.empty_like(Z)
+        d_att = torch.empty(P, D, dtype=torch.float32, device=Z.device) if ctx.mode == 0 else None
+        need = int(_lib.query('peagnn_fuse_workspace_floats', n, P, D)) if ctx.mode == 0 else 0
+        ws = _ws(need, Z.device) if ctx.mode == 0 else None
+        with torch.cuda.device(Z.device):
+            _lib.call('peagnn_fuse_backward', _ptr(Z), P * D, n, P, D, _ptr(att2), ctx.mode, _ptr(dout), dout.stride(0),
+                      _ptr(dZ), P * D, _ptr(d_att), _ptr(ws), need, _stream())
+        return dZ, (d_att.reshape(ctx.att_shape) if d_att is not None else None), None, None
+
+
+def fuse_channels(Z, att, mode='att', skip=None):
+    return _Fuse.apply(Z, att, 0 if mode == 'att' else 1, -1 if skip is None else int(skip))
+
+
+# ---------------------------------------------------------------------------------------------
+# K6  scoring + BPR (+ entity-aware term)
+# ---------------------------------------------------------------------------------------------
+def predict_raw(repr_, unids, inids, fc1_w, fc1_b, fc2_w, fc2_b):
+    repr_ = _rows(_req(repr_, 'cached_repr'))
+    unids, inids = unids.contiguous(), inids.contiguous()
+    if unids.dtype != torch.long or inids.dtype != torch.long:
+        raise TypeError('node ids must be int64 (torch.long)')
+    B = int(unids.numel())
+    out = torch.empty(B, 1, dtype=torch.float32, device=repr_.device)
+    with torch.cuda.device(repr_.device):
+        _lib.call('peagnn_predict', _ptr(repr_), repr_.stride(0), repr_.shape[1], _ptr(unids), _ptr(inids), B,
+                  _ptr(fc1_w.contiguous()), _ptr(fc1_b.contiguous()), _ptr(fc2_w.contiguous()), _ptr(fc2_b.contiguous()),
+                  _ptr(out), _stream())
+    return out
+
+
+class _Predict(torch.autograd.Function):
+    """predict() outside loss(): forward-only on the kernel path.  (Training goes through
+    _BprLoss, which fuses scoring and loss; upstream never differentiates predict() directly.)"""
+
+    @staticmethod
+    def forward(ctx, repr_, unids, inids, fc1_w, fc1_b, fc2_w, fc2_b):
+        return predict_raw(repr_, unids, inids, fc1_w, fc1_b, fc2_w, fc2_b)
+
+    @staticmethod
+    def backward(ctx, g):
+        raise RuntimeError('predict() is forward-only here; differentiate loss() instead')
+
+
+class _BprLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, repr_, fc1_w, fc1_b, fc2_w, fc2_b, batch):
+        repr_ = _rows(_req(repr_, 'cached_repr'))
+        batch = batch.contiguous()
+        if batch.dtype != torch.long or batch.dim() != 2 or batch.shape[1] < 3:
+            raise ValueError('batch must be a LongTensor [B, >=3]')
+        B, cols = int(batch.shape[0]), int(batch.shape[1])
+        D = repr_.shape[1]
+        dev = repr_.device
+        need_grad = any(ctx.needs_input_grad[:5])
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        need = int(_lib.query('peagnn_bpr_workspace_floats', B, D))
+        ws = _ws(need, dev)
+        fc1_w, fc1_b, fc2_w, fc2_b = (t.contiguous() for t in (fc1_w, fc1_b, fc2_w, fc2_b))
+        if need_grad:
+            d_repr = torch.zeros_like(repr_)
+            g1w, g1b, g2w, g2b = (torch.empty_like(t) for t in (fc1_w, fc1_b, fc2_w, fc2_b))
+        else:
+            d_repr = g1w = g1b = g2w = g2b = None
+        with torch.cuda.device(dev):
+            _lib.call('peagnn_bpr_loss', _ptr(repr_), repr_.stride(0), D, _ptr(batch), cols, B,
+                      _ptr(fc1_w), _ptr(fc1_b), _ptr(fc2_w), _ptr(fc2_b), _ptr(loss), int(need_grad),
+                      _ptr(d_repr), d_repr.stride(0) if need_grad else 0, _ptr(g1w), _ptr(g1b), _ptr(g2w), _ptr(g2b),
+                      _ptr(ws), need, _stream())
+        if need_grad:
+            ctx.save_for_backward(d_repr, g1w, g1b, g2w, g2b)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        d_repr, g1w, g1b, g2w, g2b = ctx.saved_tensors
+        return d_repr * g, g1w * g, g1b * g, g2w * g, g2b * g, None
+
+
+class _EntityReg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, batch, coff):
+        x = _rows(_req(x, 'x'))
+        batch = batch.contiguous()
+        if batch.dtype != torch.long or batch.dim() != 2 or batch.shape[1] != 9:
+            raise ValueError('entity-aware batches are LongTensor [B, 9] (datasets/movielens.py:1179)')
+        B = int(batch.shape[0])
+        dev = x.device
+        need_grad = ctx.needs_input_grad[0]
+        loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        dx = torch.zeros_like(x) if need_grad else None
+        ws = _ws(B, dev)
+        with torch.cuda.device(dev):
+            _lib.call('peagnn_entity_reg', _ptr(x), x.stride(0), x.shape[1], _ptr(batch), B, float(coff), _ptr(loss),
+                      int(need_grad), _ptr(dx), dx.stride(0) if need_grad else 0, _ptr(ws), B, _stream())
+        if need_grad:
+            ctx.save_for_backward(dx)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dx,) = ctx.saved_tensors
+        return dx * g, None, None
+
+
+def bpr_loss(repr_, fc1_w, fc1_b, fc2_w, fc2_b, batch):
+    return _BprLoss.apply(repr_, fc1_w, fc1_b, fc2_w, fc2_b, batch)
+
+
+def entity_reg(x, batch, coff):
+    """coff * (item_reg + user_reg) of models/base.py:50-76 (already scaled by coff)."""
+    return _EntityReg.apply(x, batch, coff)
+
+
+# ---------------------------------------------------------------------------------------------
+# K7  evaluation
+# ---------------------------------------------------------------------------------------------
+def eval_rank(repr_, users, cand, n_pos, fc1_w, fc1_b, fc2_w, fc2_b, return_scores=False):
+    """per-user fp64 [U, 36] rows (HR[16] | NDCG[16] | AUC | loss | first-hit rank | 0) and their
+    column means, all on the device; optionally the raw scores [U, C]."""
+    repr_ = _rows(_req(repr_, 'cached_repr'))
+    users, cand = users.contiguous(), cand.contiguous()
+    U, Cn = int(cand.shape[0]), int(cand.shape[1])
+    dev = repr_.device
+    per_user = torch.empty(U, 36, dtype=torch.float64, device=dev)
+    scores = torch.empty(U, Cn, dtype=torch.float32, device=dev) if return_scores else None
+    means = torch.empty(36, dtype=torch.float64, device=dev)
+    ws = torch.empty(148 * 36, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call('peagnn_eval_rank', _ptr(repr_), repr_.stride(0), repr_.shape[1], _ptr(users), _ptr(cand), U, Cn,
+                  int(n_pos), _ptr(fc1_w.contiguous()), _ptr(fc1_b.contiguous()), _ptr(fc2_w.contiguous()),
+                  _ptr(fc2_b.contiguous()), _ptr(per_user), _ptr(scores), _stream())
+        _lib.call('peagnn_column_mean', _ptr(per_user), 36, U, 36, _ptr(means), _ptr(ws), ws.numel(), _stream())
+    return per_user, means, scores

@@ -1,0 +1,157 @@
+"""PEAGNN model core - drop-in for reference ``graph_recsys_benchmark/models/base.py``:
+``GraphRecsysModel`` (:29-96: loss / eval), ``PEABaseChannel`` (:129-140) and
+``PEABaseRecsysModel`` (:143-214: embedding table, P channels, fusion, pair-MLP predict).
+
+Same constructor kwargs, attributes, state_dict keys and method semantics; every tensor
+operation is a libpeagnn_sm100 kernel (functional.py).  What changes underneath:
+  * each distinct relation is turned into CSR/CSC once (graph.py) instead of being re-derived by
+    PyG on every conv call;
+  * first-step aggregations of the raw embedding table are shared between metapaths that start
+    with the same relation (A_hat @ x does not depend on the channel's weights);
+  * scoring + BPR loss (+ the entity-aware term) are one fused call.
+"""
+import torch
+from torch.nn import Parameter
+
+from ..nn.inits import glorot
+from .. import functional as F_
+from ..graph import get_graph
+
+
+class GraphRecsysModel(torch.nn.Module):
+    def __init__(self, **kwargs):
+        super(GraphRecsysModel, self).__init__()
+        self._init(**kwargs)
+        self.reset_parameters()
+
+    def _init(self, **kwargs):
+        raise NotImplementedError
+
+    def reset_parameters(self):
+        raise NotImplementedError
+
+    def loss(self, pos_neg_pair_t):
+        """reference models/base.py:43-80 (BPR sum + entity-aware regulariser on raw x)."""
+        if self.training:
+            self.cached_repr = self.forward()
+        cf_loss = F_.bpr_loss(self.cached_repr, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
+                              pos_neg_pair_t)
+        if self.entity_aware and self.training:
+            loss = cf_loss + F_.entity_reg(self.x, pos_neg_pair_t, self.entity_aware_coff)
+        else:
+            loss = cf_loss
+        return loss
+
+    def update_graph_input(self, dataset):
+        raise NotImplementedError
+
+    def predict(self, unids, inids):
+        raise NotImplementedError
+
+    def eval(self, metapath_idx=None):
+        """reference models/base.py:88-96: nn.Module.eval() + one no-grad propagation."""
+        super(GraphRecsysModel, self).eval()
+        if self.__class__.__name__ not in ['KGATRecsysModel', 'KGCNRecsysModel']:
+            if self.__class__.__name__[:3] == 'PEA':
+                with torch.no_grad():
+                    self.cached_repr = self.forward(metapath_idx)
+            else:
+                with torch.no_grad():
+                    self.cached_repr = self.forward()
+        return self
+
+
+class PEABaseChannel(torch.nn.Module):
+    def reset_parameters(self):
+        for module in self.gnn_layers:
+            module.reset_parameters()
+
+    def forward(self, x, edge_index_list, shared=None):
+        """relu(conv_s(x)) for every step but the last (reference models/base.py:134-140); the
+        relu is fused into the conv's epilogue.  ``shared`` memoises first-step aggregations."""
+        assert len(edge_index_list) == self.num_steps
+        n = x.size(0)
+        for step_idx in range(self.num_steps):
+            layer = self.gnn_layers[step_idx]
+            ei = edge_index_list[step_idx]
+            relu = step_idx < self.num_steps - 1
+            g = get_graph(ei, n)
+            kw = {}
+            if step_idx == 0 and shared is not None and getattr(layer, 'shares_aggregate', None):
+                key = (layer.shares_aggregate, id(g))
+                if layer.in_channels <= layer.out_channels:
+                    if key not in shared:
+                        shared[key] = layer.aggregate_input(x, g)
+                    kw['aggregated'] = shared[key]
+            x = layer(x, ei, relu=relu, graph=g, **kw)
+        return x
+
+
+class PEABaseRecsysModel(GraphRecsysModel):
+    def __init__(self, **kwargs):
+        super(PEABaseRecsysModel, self).__init__(**kwargs)
+
+    def _init(self, **kwargs):
+        self.entity_aware = kwargs['entity_aware']
+        self.entity_aware_coff = kwargs['entity_aware_coff']
+        self.meta_path_steps = kwargs['meta_path_steps']
+        self.if_use_features = kwargs['if_use_features']
+        self.channel_aggr = kwargs['channel_aggr']
+
+        # Create node embedding
+        if not self.if_use_features:
+            self.x = Parameter(torch.Tensor(kwargs['dataset']['num_nodes'], kwargs['emb_dim']))
+        else:
+            raise NotImplementedError('Feature not implemented!')
+
+        # Create graphs (COO lists exactly as the reference keeps them; CSR is derived lazily)
+        meta_path_edge_index_list = self.update_graph_input(kwargs['dataset'])
+        assert len(meta_path_edge_index_list) == len(kwargs['meta_path_steps'])
+        self.meta_path_edge_index_list = meta_path_edge_index_list
+
+        # Create channels
+        self.pea_channels = torch.nn.ModuleList()
+        for num_steps in kwargs['meta_path_steps']:
+            kwargs_cpy = kwargs.copy()
+            kwargs_cpy['num_steps'] = num_steps
+            self.pea_channels.append(kwargs_cpy['channel_class'](**kwargs_cpy))
+
+        if self.channel_aggr == 'att':
+            self.att = Parameter(torch.Tensor(1, len(kwargs['meta_path_steps']), kwargs['repr_dim']))
+
+        if self.channel_aggr == 'cat':
+            self.fc1 = torch.nn.Linear(2 * len(kwargs['meta_path_steps']) * kwargs['repr_dim'], kwargs['repr_dim'])
+        else:
+            self.fc1 = torch.nn.Linear(2 * kwargs['repr_dim'], kwargs['repr_dim'])
+        self.fc2 = torch.nn.Linear(kwargs['repr_dim'], 1)
+        self.cached_repr = None
+
+    def reset_parameters(self):
+        if not self.if_use_features:
+            glorot(self.x)
+        for module in self.pea_channels:
+            module.reset_parameters()
+        glorot(self.fc1.weight)
+        glorot(self.fc2.weight)
+        if self.channel_aggr == 'att':
+            glorot(self.att)
+
+    def channel_outputs(self):
+        x = self.x
+        shared = {}
+        return [module(x, self.meta_path_edge_index_list[idx], shared)
+                for idx, module in enumerate(self.pea_channels)]
+
+    def forward(self, metapath_idx=None):
+        """reference models/base.py:191-206.  'att' and 'mean' are the fusions that work upstream
+        ('cat' / 'concat' disagree between _init and forward there and raise)."""
+        if self.channel_aggr not in ('att', 'mean'):
+            raise NotImplementedError('Other aggr methods not implemeted!')
+        z = torch.stack(self.channel_outputs(), dim=1)                  # [N, P, repr]
+        att = self.att if self.channel_aggr == 'att' else None
+        return F_.fuse_channels(z, att, self.channel_aggr, metapath_idx)
+
+    def predict(self, unids, inids):
+        """reference models/base.py:208-214: fc2(relu(fc1([repr[u] || repr[i]]))) -> [B, 1]."""
+        return F_.predict_raw(self.cached_repr, unids, inids, self.fc1.weight, self.fc1.bias,
+                              self.fc2.weight, self.fc2.bias)

@@ -1,0 +1,245 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (functional.py is a ctypes shim).
+Oracle = oracle/ (CPU); tolerance: bit-exact for integers, 1e-5 relative (max-norm) for fp32 as
+BASELINE.json's north_star states (gradients through long fp32 sums get 1e-4)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import random_edge_index, rel_err
+from oracle import graph as ograph, pyg150
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = 'cuda'
+
+
+def _graph(ei, n, **kw):
+    from graph_recsys_benchmark_b200.graph import RelationGraph
+    return RelationGraph.from_edge_index(ei.to(DEV), n, **kw)
+
+
+@pytest.mark.parametrize('n,e,loops,multi', [(6, 0, 0, 0), (50, 400, 5, 30), (3000, 60000, 50, 1000), (10, 5000, 3, 0)])
+def test_csr_build_bit_exact(n, e, loops, multi):
+    ei = random_edge_index(n, e, 11, self_loops=loops, multi=multi)
+    g = _graph(ei, n)
+    for csr, key, val in ((g.fwd, ei[1], ei[0]), (g.bwd, ei[0], ei[1])):
+        rp, col, eid = ograph.csr_by_key(key.numpy(), val.numpy(), n, drop_self_loops=True)
+        assert np.array_equal(csr.rowptr.cpu().numpy(), rp)
+        assert np.array_equal(csr.col.cpu().numpy(), col)
+        assert np.array_equal(csr.eid.cpu().numpy(), eid)
+    if g.fwd.nnz:
+        perm = g.bwd_to_fwd.cpu().long()
+        assert torch.equal(g.fwd.eid.cpu()[perm], g.bwd.eid.cpu())
+
+
+def _conv_pair(kind, fin, fout, heads=1):
+    from graph_recsys_benchmark_b200 import nn as pnn
+    torch.manual_seed(3)
+    if kind == 'gcn':
+        o, p = pyg150.GCNConv(fin, fout), pnn.PEAGCNConv(fin, fout)
+        o.bias.data.uniform_(-0.5, 0.5)
+    elif kind == 'sage':
+        o, p = pyg150.SAGEConv(fin, fout), pnn.PEASageConv(fin, fout)
+    else:
+        o, p = pyg150.GATConv(fin, fout, heads=heads), pnn.PEAGATConv(fin, fout, heads=heads)
+        o.bias.data.uniform_(-0.5, 0.5)
+    p.load_state_dict(o.state_dict())
+    return o, p.to(DEV)
+
+
+GRAPHS = {
+    'small': dict(n=60, e=500, loops=4, multi=40),
+    'isolated': dict(n=200, e=150, loops=0, multi=0),
+    'heavy': dict(n=300, e=40000, loops=10, multi=500),      # rows far above the heavy threshold
+    'bipartite': dict(n=400, e=6000, loops=0, multi=100, src_range=(0, 100), dst_range=(100, 400)),
+}
+
+
+@pytest.mark.parametrize('kind', ['gcn', 'sage', 'gat'])
+@pytest.mark.parametrize('gname', list(GRAPHS))
+@pytest.mark.parametrize('fin,fout', [(64, 64), (64, 16), (16, 64)])
+@pytest.mark.parametrize('relu', [False, True])
+def test_conv_forward_backward(kind, gname, fin, fout, relu):
+    spec = dict(GRAPHS[gname])
+    n = spec.pop('n')
+    ei = random_edge_index(n, spec.pop('e'), 5, self_loops=spec.pop('loops'), multi=spec.pop('multi'), **spec)
+    from graph_recsys_benchmark_b200 import graph as pgraph
+    old = pgraph.HEAVY_THRESHOLD, pgraph.CHUNK_EDGES
+    if gname == 'heavy':
+        pgraph.HEAVY_THRESHOLD, pgraph.CHUNK_EDGES = 64, 96    # forces multi-chunk rows at test size
+    try:
+        pgraph.clear_cache()
+        o, p = _conv_pair(kind, fin, fout)
+        x = torch.randn(n, fin)
+        xo = x.clone().double().requires_grad_(True)
+        xp = x.clone().to(DEV).requires_grad_(True)
+        o64 = o.double()
+        yo = o64(xo, ei)
+        if relu:
+            yo = torch.relu(yo)
+        yp = p(xp, ei.to(DEV), relu=relu)
+        assert rel_err(yp, yo) < TOL
+        w = torch.randn(n, yo.shape[1])
+        (yo * w.double()).sum().backward()
+        (yp * w.to(DEV)).sum().backward()
+        assert rel_err(xp.grad, xo.grad) < 10 * TOL
+        for (name, po), (_, pp) in zip(o64.named_parameters(), p.named_parameters()):
+            assert rel_err(pp.grad, po.grad) < 10 * TOL, name
+    finally:
+        pgraph.HEAVY_THRESHOLD, pgraph.CHUNK_EDGES = old
+        pgraph.clear_cache()
+
+
+@pytest.mark.parametrize('heads', [2, 4])
+def test_gat_multi_head(heads):
+    n = 120
+    ei = random_edge_index(n, 1500, 9, self_loops=5, multi=60)
+    o, p = _conv_pair('gat', 64, 16, heads=heads)
+    x = torch.randn(n, 64)
+    xo = x.clone().double().requires_grad_(True)
+    xp = x.clone().to(DEV).requires_grad_(True)
+    o64 = o.double()
+    yo, yp = o64(xo, ei), p(xp, ei.to(DEV))
+    assert yp.shape == (n, heads * 16) and rel_err(yp, yo) < TOL
+    w = torch.randn(n, heads * 16)
+    (yo * w.double()).sum().backward()
+    (yp * w.to(DEV)).sum().backward()
+    assert rel_err(xp.grad, xo.grad) < 10 * TOL
+    for (name, po), (_, pp) in zip(o64.named_parameters(), p.named_parameters()):
+        assert rel_err(pp.grad, po.grad) < 10 * TOL, name
+
+
+def test_conv_fp32_oracle_agreement_is_rounding_level():
+    """Against the fp32 oracle the gap is rounding only (different summation order)."""
+    n = 500
+    ei = random_edge_index(n, 20000, 2, multi=300)
+    o, p = _conv_pair('gcn', 64, 64)
+    x = torch.randn(n, 64)
+    assert rel_err(p(x.to(DEV), ei.to(DEV)), o(x, ei)) < TOL
+
+
+@pytest.mark.parametrize('P,D,mode', [(9, 16, 'att'), (13, 16, 'att'), (11, 16, 'mean'), (1, 16, 'att'), (9, 64, 'att'), (5, 8, 'att')])
+def test_fuse(P, D, mode):
+    from graph_recsys_benchmark_b200 import functional as F_
+    n = 777
+    z = torch.randn(n, P, D)
+    att = torch.randn(1, P, D) * 0.5
+    zo = z.clone().double().requires_grad_(True)
+    ao = att.clone().double().requires_grad_(True)
+    zp = z.clone().to(DEV).requires_grad_(True)
+    ap = att.clone().to(DEV).requires_grad_(True)
+    if mode == 'att':
+        w = torch.softmax((zo * ao).sum(-1), dim=-1).unsqueeze(-1)
+        ro = (zo * w).sum(1)
+    else:
+        ro = zo.mean(1)
+    rp = F_.fuse_channels(zp, ap if mode == 'att' else None, mode)
+    assert rel_err(rp, ro) < TOL
+    g = torch.randn(n, D)
+    (ro * g.double()).sum().backward()
+    (rp * g.to(DEV)).sum().backward()
+    assert rel_err(zp.grad, zo.grad) < 10 * TOL
+    if mode == 'att':
+        assert rel_err(ap.grad, ao.grad) < 10 * TOL
+
+
+@pytest.mark.parametrize('skip', [0, 4, 8])
+def test_fuse_ablation(skip):
+    from graph_recsys_benchmark_b200 import functional as F_
+    n, P, D = 300, 9, 16
+    z = torch.randn(n, P, D)
+    att = torch.randn(1, P, D)
+    zz = z.clone().double()
+    zz[:, skip] = 0
+    w = torch.softmax((zz * att.double()).sum(-1), dim=-1).unsqueeze(-1)
+    ro = (zz * w).sum(1)
+    with torch.no_grad():
+        rp = F_.fuse_channels(z.to(DEV), att.to(DEV), 'att', skip)
+    assert rel_err(rp, ro) < TOL
+
+
+def _fc(D):
+    torch.manual_seed(4)
+    return torch.nn.Linear(2 * D, D), torch.nn.Linear(D, 1)
+
+
+@pytest.mark.parametrize('B', [1, 37, 1024, 4096])
+def test_bpr_loss_and_grads(B):
+    from graph_recsys_benchmark_b200 import functional as F_
+    n, D = 500, 16
+    fc1, fc2 = _fc(D)
+    r = torch.randn(n, D)
+    batch = torch.randint(0, n, (B, 3))
+    ro = r.clone().double().requires_grad_(True)
+    f1, f2 = torch.nn.Linear(2 * D, D).double(), torch.nn.Linear(D, 1).double()
+    f1.load_state_dict(fc1.state_dict()); f2.load_state_dict(fc2.state_dict())
+
+    def pred(u, i):
+        return f2(torch.relu(f1(torch.cat([ro[u], ro[i]], dim=-1))))
+    lo = -(pred(batch[:, 0], batch[:, 1]) - pred(batch[:, 0], batch[:, 2])).sigmoid().log().sum()
+    lo.backward()
+    rp = r.clone().to(DEV).requires_grad_(True)
+    ps = [t.detach().clone().to(DEV).requires_grad_(True) for t in (fc1.weight, fc1.bias, fc2.weight, fc2.bias)]
+    lp = F_.bpr_loss(rp, ps[0], ps[1], ps[2], ps[3], batch.to(DEV))
+    lp.backward()
+    assert abs(lp.item() - lo.item()) / abs(lo.item()) < TOL
+    assert rel_err(rp.grad, ro.grad) < 10 * TOL
+    for pp, po in zip(ps, (f1.weight, f1.bias, f2.weight, f2.bias)):
+        assert rel_err(pp.grad, po.grad) < 10 * TOL or float(po.grad.abs().max()) < 1e-12
+    # predict()
+    sp = F_.predict_raw(rp.detach(), batch[:, 0].to(DEV), batch[:, 1].to(DEV), ps[0], ps[1], ps[2], ps[3])
+    assert sp.shape == (B, 1) and rel_err(sp, pred(batch[:, 0], batch[:, 1])) < TOL
+
+
+def test_entity_regulariser():
+    from graph_recsys_benchmark_b200 import functional as F_
+    n, E, B = 400, 64, 513
+    x = torch.randn(n, E) * 0.3
+    batch = torch.randint(0, n, (B, 9))
+    batch[:, 5] = torch.randint(0, 2, (B,))
+    batch[:, 8] = torch.randint(0, 2, (B,))
+    xo = x.clone().double().requires_grad_(True)
+
+    def sq(a, b):
+        d = xo[a] - xo[b]
+        return (d * d).sum(-1)
+    it = (sq(batch[:, 1], batch[:, 3]) - sq(batch[:, 1], batch[:, 4])) * batch[:, 5]
+    us = (sq(batch[:, 0], batch[:, 6]) - sq(batch[:, 0], batch[:, 7])) * batch[:, 8]
+    lo = 0.1 * (-it.sigmoid().log().sum() - us.sigmoid().log().sum())
+    lo.backward()
+    xp = x.clone().to(DEV).requires_grad_(True)
+    lp = F_.entity_reg(xp, batch.to(DEV), 0.1)
+    lp.backward()
+    assert abs(lp.item() - lo.item()) / abs(lo.item()) < TOL
+    assert rel_err(xp.grad, xo.grad) < 10 * TOL
+
+
+@pytest.mark.parametrize('U,C,n_pos', [(1, 100, 1), (613, 100, 1), (50, 20, 3), (5, 1000, 1)])
+def test_eval_rank_matches_reference_metrics(U, C, n_pos):
+    from graph_recsys_benchmark_b200 import functional as F_
+    from oracle import rec_utils
+    n, D = 2000, 16
+    fc1, fc2 = _fc(D)
+    r = torch.randn(n, D)
+    users = torch.randint(0, n, (U,))
+    cand = torch.randint(0, n, (U, C))
+    cand[:, n_pos + 3] = cand[:, n_pos + 2]          # duplicated negatives tie with each other
+    args = [t.detach().to(DEV) for t in (fc1.weight, fc1.bias, fc2.weight, fc2.bias)]
+    per_user, means, scores = F_.eval_rank(r.to(DEV), users.to(DEV), cand.to(DEV), n_pos, *args, return_scores=True)
+    s = scores.cpu()
+    # scores against the fp64 MLP
+    f1, f2 = fc1.double(), fc2.double()
+    ref = f2(torch.relu(f1(torch.cat([r.double()[users].unsqueeze(1).expand(-1, C, -1), r.double()[cand]], dim=-1)))).squeeze(-1)
+    assert rel_err(s, ref) < TOL
+    # ranking / metrics: reference procedure (solvers.py:88-96) applied to the SAME fp32 scores -> bit-exact
+    pu = per_user.cpu().numpy()
+    for k in range(U):
+        _, idx = torch.sort(s[k], descending=True, stable=True)
+        hit_vec = (idx < n_pos).numpy()
+        assert np.array_equal(pu[k, :16], np.array(rec_utils.hit(hit_vec), dtype=np.float64))
+        assert np.allclose(pu[k, 16:32], np.array(rec_utils.ndcg(hit_vec)), rtol=1e-14, atol=0)
+        assert pu[k, 32] == rec_utils.auc(s[k, :n_pos].numpy(), s[k, n_pos:].numpy())
+        assert int(pu[k, 34]) == int(np.argmax(hit_vec))
+        pair = -(s[k, :n_pos].double().view(-1, 1) - s[k, n_pos:].double().view(1, -1)).sigmoid().log().sum()
+        assert abs(pu[k, 33] - pair.item()) <= 1e-5 * abs(pair.item())
+    assert np.allclose(means.cpu().numpy(), pu.mean(axis=0), rtol=1e-12, atol=1e-15)
