@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py - BPR triples/s of one PEAGNN train step at the MovieLens-25M shape (BASELINE.json),
+plus the HBM roofline of the metapath aggregation kernels.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl product|reference]
+                  [--workload ml-25m] [--model gcn|gat|sage] [--batch 4096]
+
+A "step" = one pass of the hot path over one batch of synthetic input: full-graph propagation
+over every metapath (forward + backward), fused scoring + BPR loss, Adam step - exactly what
+reference solvers.py:213-218 does per batch.  One JSON line on stdout (rank 0).
+
+  value     device-resident batches, CUDA-event timed, max over ranks
+  e2e       the same step through the public model API with the batch in pinned HOST memory
+            (H2D copy inside the timed region) and the loss read back to the host every step
+  roofline  all launches of the aggregation entry point (peagnn_spmm / peagnn_gat_aggregate)
+            inside the timed region: algorithmic bytes / event-timed duration
+  cpu_baseline / --impl reference   the CPU oracle restatement of the reference path on the
+            host cores, on a 1/10-edge sample of the same workload, scaled by the work ratio
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+LITE = {'ml-25m': 'ml-25m-lite', 'yelp': 'yelp-lite', 'ml-small': 'ml-small', 'tiny': 'tiny',
+        'ml-25m-lite': 'ml-25m-lite', 'yelp-lite': 'yelp-lite'}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='product', choices=['product', 'reference'])
+    ap.add_argument('--workload', default='ml-25m')
+    ap.add_argument('--model', default='gcn', choices=['gcn', 'gat', 'sage'])
+    ap.add_argument('--batch', type=int, default=4096)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--prewarm', type=float, default=2.0, help='seconds of untimed steps before the warm-up')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu, self.lines, self.proc = gpu_index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def work_units(ds):
+    """sum over (metapath, step) of (E + N) * width - the work ratio used to scale a CPU sample."""
+    from graph_recsys_benchmark_b200.utils import metapath_table
+    tab = metapath_table({'dataset': ds.dataset, 'name': ds.name})
+    total = 0
+    for path in tab:
+        for s, (rel, _) in enumerate(path):
+            total += (ds.edge_index_nps[rel].shape[1] + ds.num_nodes) * (64 if s == 0 else 16)
+    return total
+
+
+def make_batches(ds, B, count, seed):
+    """count x [B, 3] BPR triples: positives drawn from user2item, negatives as the reference's
+    'random' strategy (np.random.randint over the item id range, movielens.py:923-927)."""
+    rng = np.random.RandomState(seed)
+    u2i = ds.edge_index_nps['user2item']
+    sel = rng.randint(0, u2i.shape[1], size=(count, B))
+    neg = rng.randint(ds.type_accs['iid'], ds.type_accs['iid'] + ds.num_iids, size=(count, B))
+    out = np.stack([u2i[0][sel].astype(np.int64), u2i[1][sel].astype(np.int64), neg.astype(np.int64)], axis=-1)
+    return torch.from_numpy(out)
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_oracle_steps(workload, kind, B, steps, warmup, threads):
+    """Times the CPU oracle (pure-torch restatement of the reference's PyG path) on the lite
+    sample of the workload; returns (seconds per step on the sample, work ratio full/sample, info)."""
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+    from helpers import oracle_model_for
+    torch.set_num_threads(threads)
+    lite = LITE.get(workload, workload)
+    ds = SyntheticHIN(lite, seed=1234)
+    torch.manual_seed(2020)
+    model = oracle_model_for(ds, kind)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3)
+    batches = make_batches(ds, B, steps + warmup, seed=7)
+    model.train()
+    times = []
+    for k in range(steps + warmup):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = model.loss(batches[k])
+        loss.backward()
+        opt.step()
+        loss.item()
+        if k >= warmup:
+            times.append(time.perf_counter() - t0)
+    return float(np.mean(times)), ds, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from graph_recsys_benchmark_b200.datasets import SHAPES
+    threads = os.cpu_count() or 1
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
+    t_lite, ds_lite, times = cpu_oracle_steps(args.workload, args.model, args.batch, steps, warmup, threads)
+    ratio = full_over_lite_ratio(args.workload, ds_lite)
+    t_full = t_lite * ratio
+    value = args.batch / t_full
+    sample = ('%d step(s) of the CPU oracle (oracle/: pure-torch restatement of the PyG-1.5.0 path) on the %s graph '
+              '(%.1f s/step), scaled by the (E+N)*width work ratio %.2f to %s'
+              % (steps, LITE.get(args.workload), t_lite, ratio, args.workload))
+    line = {
+        'impl': 'reference', 'metric': 'bpr_triples_per_sec', 'value': value, 'unit': 'triples/s',
+        'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': t_full * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args),
+        'cpu_baseline': {'value': value, 'unit': 'triples/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'triples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def full_over_lite_ratio(workload, ds_lite):
+    """(E+N)*width work of the full workload over the lite sample, from the shape tables alone
+    (edge counts of the full graph are estimated by the interaction ratio when it is not built)."""
+    from graph_recsys_benchmark_b200.datasets import SHAPES
+    if LITE.get(workload, workload) == workload:
+        return 1.0
+    full, lite = SHAPES[workload], SHAPES[LITE[workload]]
+    return float(full['interactions']) / float(lite['interactions'])
+
+
+def workload_config(args):
+    return {'workload': '%s / PEA%s BPR train step, 13 metapaths x 2 steps, emb 64, hidden 64, repr 16'
+                        % (args.workload, args.model.upper()) if args.workload.startswith('ml-25m') else
+                        '%s / PEA%s BPR train step' % (args.workload, args.model.upper()),
+            'batch_per_gpu': args.batch, 'optimizer': 'Adam(lr=1e-3, weight_decay=1e-3, fused)',
+            'negatives': 'random', 'l2_between_iterations': 'inputs larger than L2 (CSR + activations > 126 MB)'}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_product(args):
+    import torch.distributed as dist
+    from graph_recsys_benchmark_b200 import _lib, functional as F_
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+    from helpers import product_model_for
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    ds = SyntheticHIN(args.workload, seed=1234)
+    torch.manual_seed(2020)
+    model = product_model_for(ds, args.model, device=dev)
+    params = [p for p in model.parameters()]
+    opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-3, fused=True)
+    model.train()
+    K, W, B = args.steps, args.warmup, args.batch
+    host_batches = make_batches(ds, B, K + W, seed=100 + rank).pin_memory()
+    dev_batches = host_batches.to(dev)
+
+    def allreduce_grads():
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            off = 0
+            for p in params:
+                n = p.numel()
+                p.grad.copy_(flat[off:off + n].view_as(p))
+                off += n
+
+    def step(batch):
+        opt.zero_grad(set_to_none=True)
+        loss = model.loss(batch)
+        loss.backward()
+        allreduce_grads()
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # bring the SM clocks out of idle before anything is timed (the graph build above is host work)
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < args.prewarm:
+        step(dev_batches[0])
+        torch.cuda.synchronize()
+    for k in range(W):
+        step(dev_batches[k])
+    barrier()
+
+    # ---- leg 1: device-resident batches (value + roofline) ---------------------------------
+    F_.PROFILE = []
+    _lib.profile = []
+    launches0 = _lib.load().peagnn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for k in range(K):
+            step(dev_batches[W + k])
+        e1.record()
+        barrier()
+    launches = int(_lib.load().peagnn_launch_count() - launches0)
+    ms_total = e0.elapsed_time(e1)
+    prof_spmm, prof_all = F_.PROFILE, _lib.profile
+    F_.PROFILE = None
+    _lib.profile = None
+
+    # ---- leg 2: end to end through the public API with host batches -------------------------
+    barrier()
+    t_e2e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_e2e[0].record()
+    last = 0.0
+    for k in range(K):
+        b = host_batches[W + k].to(dev, non_blocking=True)        # H2D inside the timed region
+        last = step(b).item()                                      # D2H read of the loss every step
+    t_e2e[1].record()
+    barrier()
+    ms_e2e = t_e2e[0].elapsed_time(t_e2e[1])
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0].item()), float(t[1].item())
+
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+        peak_src = 'measured' if 'hbm_gbs' in peaks else 'fallback'
+        agg_bytes = sum(p[1] for p in prof_spmm)
+        agg_ms = sum(p[2].elapsed_time(p[3]) for p in prof_spmm)
+        by_name = {}
+        for name, a, b in prof_all:
+            d = by_name.setdefault(name, [0, 0.0])
+            d[0] += 1
+            d[1] += a.elapsed_time(b)
+        agg_name = 'peagnn_gat_aggregate' if args.model == 'gat' else 'peagnn_spmm'
+        if args.model == 'gat':        # GAT: time of the aggregate entry point; bytes from the SURVEY formula
+            agg_ms = by_name.get(agg_name, [0, 0.0])[1]
+            agg_bytes = None
+        achieved = (agg_bytes / (agg_ms * 1e-3) / 1e9) if (agg_bytes and agg_ms > 0) else None
+        breakdown = {k: {'calls_per_step': v[0] / K, 'ms_per_step': v[1] / K} for k, v in sorted(by_name.items())}
+        line = {
+            'metric': 'bpr_triples_per_sec', 'value': world * B * K / (ms_total * 1e-3), 'unit': 'triples/s',
+            'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': dict(workload_config(args), num_nodes=ds.num_nodes,
+                           edges_user2item=int(ds.edge_index_nps['user2item'].shape[1]),
+                           parallelism='dp%d (replicated propagation, NCCL allreduce of gradients)' % world
+                           if world > 1 else 'single GPU'),
+            'e2e': {'value': world * B * K / (ms_e2e * 1e-3), 'unit': 'triples/s', 'h2d_bytes_per_step': B * 3 * 8,
+                    'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / K, 'last_loss': last},
+            'gpu_launches': launches,
+            'roofline': {'bound': 'hbm', 'kernel': agg_name + ' (csr_rows_kernel / csr_chunk_kernel)',
+                         'achieved': achieved, 'peak': hbm_peak, 'peak_source': peak_src, 'unit': 'GB/s',
+                         'frac': (achieved / hbm_peak) if achieved else None, 'traffic': None,
+                         'launches_per_step': len(prof_spmm) / K if prof_spmm else None,
+                         'ms_per_step': agg_ms / K,
+                         'share_of_step': agg_ms / ms_total if ms_total > 0 else None},
+            'breakdown_ms_per_step': breakdown,
+            'clocks': clocks.summary(),
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            t_lite, ds_lite, _ = cpu_oracle_steps(args.workload, args.model, B, 1, 1 if LITE.get(args.workload) != 'ml-25m-lite' else 0, threads)
+            ratio = full_over_lite_ratio(args.workload, ds_lite)
+            line['cpu_baseline'] = {
+                'value': B / (t_lite * ratio), 'unit': 'triples/s', 'cores': threads, 'kind': 'port',
+                'sample': '1 train step of the CPU oracle on the %s graph (%.1f s), scaled by the interaction ratio %.1f'
+                          % (LITE.get(args.workload), t_lite, ratio)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -32,6 +32,7 @@ _G = C.POINTER(CsrView)
 SIGNATURES = {
     'peagnn_version': (_INT, []),
     'peagnn_last_error': (C.c_char_p, []),
+    'peagnn_launch_count': (C.c_ulonglong, []),
     'peagnn_csr_workspace_bytes': (_SZ, [_I64, _I32]),
     'peagnn_csr_build': (_INT, [_P, _P, _I64, _I32, _INT, _P, _P, _P, _P, _SZ, _P]),
     'peagnn_degree_scale': (_INT, [_P, _I32, _F, _F, _INT, _P, _P]),
@@ -88,10 +89,21 @@ def last_error():
     return load().peagnn_last_error().decode('utf-8', 'replace')
 
 
+profile = None      # when a list: every call appends (entry point, start event, end event)
+
+
 def call(name, *args):
     """Invoke an int-returning entry point; raise on a non-zero code."""
     global launch_count
-    rc = getattr(load(), name)(*args)
+    if profile is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(load(), name)(*args)
+        e1.record()
+        profile.append((name, e0, e1))
+    else:
+        rc = getattr(load(), name)(*args)
     launch_count += 1
     if rc != 0:
         raise RuntimeError('%s failed (%d): %s' % (name, rc, last_error()))

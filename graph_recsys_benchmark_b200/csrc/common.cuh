@@ -11,7 +11,10 @@ namespace peagnn {
 
 void set_error(const char* fmt, ...);
 
+extern unsigned long long g_launches;  // kernels launched by this library in this process
+
 inline int check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));

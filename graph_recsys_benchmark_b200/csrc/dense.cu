@@ -407,13 +407,13 @@ __global__ void __launch_bounds__(256) colmean_stage1(const double* __restrict__
     partial[(size_t)blockIdx.x * cols + threadIdx.x] = t;
   }
 }
-__global__ void colmean_stage2(const double* __restrict__ partial, int n_parts, int cols, double inv_n,
+__global__ void colmean_stage2(const double* __restrict__ partial, int n_parts, int cols, double n_rows_d,
                                double* __restrict__ out) {
   const int c = threadIdx.x;
   if (c >= cols) return;
   double s = 0.0;
   for (int p = 0; p < n_parts; ++p) s += partial[(size_t)p * cols + c];
-  out[c] = s * inv_n;
+  out[c] = s / n_rows_d;
 }
 
 }  // namespace peagnn
@@ -566,6 +566,6 @@ extern "C" int peagnn_column_mean(const double* A, int64_t lda, int64_t n, int32
   colmean_stage1<<<parts, 256, 0, stream>>>(A, lda, n, cols, rows_per_cta, workspace);
   int rc = check_launch("peagnn_column_mean(stage1)");
   if (rc) return rc;
-  colmean_stage2<<<1, 64, 0, stream>>>(workspace, parts, cols, 1.0 / (double)n, out);
+  colmean_stage2<<<1, 64, 0, stream>>>(workspace, parts, cols, (double)n, out);
   return check_launch("peagnn_column_mean(stage2)");
 }

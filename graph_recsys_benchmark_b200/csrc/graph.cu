@@ -10,6 +10,8 @@ namespace peagnn {
 
 static thread_local char g_err[512] = "";
 
+unsigned long long g_launches = 0;
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -86,6 +88,7 @@ using namespace peagnn;
 
 extern "C" int peagnn_version(void) { return 100; }
 extern "C" const char* peagnn_last_error(void) { return g_err; }
+extern "C" unsigned long long peagnn_launch_count(void) { return g_launches; }
 
 extern "C" size_t peagnn_csr_workspace_bytes(int64_t E, int32_t N) {
   if (E <= 0) return 256;

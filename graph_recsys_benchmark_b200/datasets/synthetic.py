@@ -87,6 +87,14 @@ def _zipf_weights(n, offset, expo, rng):
     return w[rng.permutation(n)]          # popularity is not correlated with the node id
 
 
+def _sorted_unique(key):
+    key = np.sort(key)
+    keep = np.empty(key.shape[0], dtype=bool)
+    keep[:1] = True
+    np.not_equal(key[1:], key[:-1], out=keep[1:])
+    return key[keep]
+
+
 def _sample(weights, size, rng):
     cdf = np.cumsum(weights)
     cdf[-1] = 1.0
@@ -132,9 +140,9 @@ class SyntheticHIN(object):
         pop = _zipf_weights(I, 30.0 if I > 1000 else 5.0, spec.get('item_zipf', 1.0), rng)
         users = np.repeat(np.arange(U, dtype=np.int64), cnt)
         items = _sample(pop, users.shape[0], rng)
-        key = np.unique(users * I + items)                         # a user rates an item once
+        key = _sorted_unique(users * I + items)                    # a user rates an item once
         users, items = key // I, key % I
-        order = np.lexsort((rng.random(users.shape[0]), users))    # "timestamp" order inside a user
+        order = np.argsort(users + rng.random(users.shape[0]))     # "timestamp" order inside a user
         users, items = users[order], items[order]
         ucount = np.bincount(users, minlength=U)
         assert ucount.min() >= 2, 'every user needs a train and a held-out interaction'
@@ -180,7 +188,7 @@ class SyntheticHIN(object):
         k = rng.integers(0, max_per_item + 1, size=I)
         it = np.repeat(np.arange(I, dtype=np.int64), k)
         who = _sample(_zipf_weights(n, 3.0, 1.0, rng), it.shape[0], rng)
-        key = np.unique(it * n + who)                              # listed once per item, item-major order
+        key = _sorted_unique(it * n + who)                              # listed once per item, item-major order
         return key % n, key // n
 
     def _movielens_features(self, spec, rng):
@@ -191,7 +199,7 @@ class SyntheticHIN(object):
         ng = 1 + rng.binomial(3, 0.43, size=I)                     # ~2.3 genres per item
         gi = np.repeat(all_i, ng)
         gg = _sample(_zipf_weights(self.num_genres, 2.0, 0.8, rng), gi.shape[0], rng)
-        key = np.unique(gg * I + gi)                               # genre-major order (movielens.py:238-244)
+        key = _sorted_unique(gg * I + gi)                               # genre-major order (movielens.py:238-244)
         ei['genre2item'] = self._rel('genre', key // I, 'iid', key % I)
         feats = {'year': ei['year2item'], 'genre': ei['genre2item']}
         for kind, mx in (('director', 1), ('actor', 4), ('writer', 2)):
@@ -211,7 +219,7 @@ class SyntheticHIN(object):
             g_items = rng.choice(I, size=n_items, replace=False)
             gi = np.repeat(g_items.astype(np.int64), G // n_items)
             gt = rng.integers(0, self.num_genome_tids, size=gi.shape[0])
-            key = np.unique(gi * self.num_genome_tids + gt)
+            key = _sorted_unique(gi * self.num_genome_tids + gt)
             ei['genome_tag2item'] = self._rel('genome_tid', key % self.num_genome_tids, 'iid', key // self.num_genome_tids)
             feats['genome'] = ei['genome_tag2item']
         # entity-aware feature lists, in the reference's order (movielens.py:946-992):
@@ -233,7 +241,7 @@ class SyntheticHIN(object):
             it = np.repeat(all_i, k)
             n = self.num_nodes_dict[t]
             who = _sample(_zipf_weights(n, 3.0, 1.0, rng), it.shape[0], rng)
-            key = np.unique(it * n + who)
+            key = _sorted_unique(it * n + who)
             ei[name] = self._rel(t, key % n, 'iid', key // n)
         ei['reviewcount2user'] = self._rel('user_reviewcount', one('user_reviewcount', U), 'uid', all_u)
         ei['friendcount2user'] = self._rel('user_friendcount', one('user_friendcount', U), 'uid', all_u)

@@ -39,11 +39,41 @@ def _ws(n, device):
 # ---------------------------------------------------------------------------------------------
 # raw launches
 # ---------------------------------------------------------------------------------------------
+PROFILE = None     # bench.py sets this to a list: (kernel family, algorithmic bytes, start event, end event)
+
+
+def _timed(name, nbytes, fn):
+    if PROFILE is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    PROFILE.append((name, nbytes, e0, e1))
+
+
+def spmm_algorithmic_bytes(nnz, nrows, feat, has_rs, has_cs, self_loop, accumulate=False):
+    """every gathered row counted as if it came from HBM, int32 indices,
+    fp32 rows: E*(4 col + 4 cs[src] + F*4) + N*(F*4 own row + 4 rs[i] + F*4 write) + (N+1)*4."""
+    per_edge = 4 + (4 if has_cs else 0) + 4 * feat
+    per_row = (4 * feat if self_loop else 0) + (4 if has_rs else 0) + 4 * feat + (4 * feat if accumulate else 0)
+    return nnz * per_edge + nrows * per_row + (nrows + 1) * 4
+
+
 def spmm_raw(csr, X, feat, out, rs=None, cs=None, self_loop=False, bias=None, relu=False, accumulate=False):
     view = csr.view(feat)
-    with torch.cuda.device(X.device):
-        _lib.call('peagnn_spmm', C.byref(view), _ptr(X), X.stride(0), feat, _ptr(out), out.stride(0),
-                  _ptr(rs), _ptr(cs), int(self_loop), _ptr(bias), int(relu), int(accumulate), _stream())
+
+    def launch():
+        with torch.cuda.device(X.device):
+            _lib.call('peagnn_spmm', C.byref(view), _ptr(X), X.stride(0), feat, _ptr(out), out.stride(0),
+                      _ptr(rs), _ptr(cs), int(self_loop), _ptr(bias), int(relu), int(accumulate), _stream())
+    if PROFILE is None:
+        launch()
+    else:
+        nrows = view.nrows
+        nnz = csr.nnz if hasattr(csr, 'nnz') else int(csr.rowptr[-1].item() - csr.rowptr[0].item())
+        _timed('spmm_f%d' % feat, spmm_algorithmic_bytes(nnz, nrows, feat, rs is not None, cs is not None,
+                                                         self_loop, accumulate), launch)
     return out
 
 

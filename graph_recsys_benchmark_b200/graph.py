@@ -182,11 +182,17 @@ class RelationGraph(object):
         self._t = None
 
     @classmethod
-    def from_edge_index(cls, edge_index, num_nodes, heavy_threshold=None, chunk_edges=None):
+    def from_edge_index(cls, edge_index, num_nodes, heavy_threshold=None, chunk_edges=None, drop_self_loops=True):
         src, dst = edge_index[0], edge_index[1]
-        fwd = build_csr(dst, src, num_nodes, True, heavy_threshold, chunk_edges)
-        bwd = build_csr(src, dst, num_nodes, True, heavy_threshold, chunk_edges)
+        fwd = build_csr(dst, src, num_nodes, drop_self_loops, heavy_threshold, chunk_edges)
+        bwd = build_csr(src, dst, num_nodes, drop_self_loops, heavy_threshold, chunk_edges)
         return cls(fwd, bwd, num_nodes, int(edge_index.shape[1]))
+
+    @property
+    def has_no_self_loops(self):
+        """True when no edge was dropped at build time, i.e. the relation has no self-loop edges
+        (all PEAGNN relations are bipartite) and one structure serves all three conv families."""
+        return self.fwd.nnz == self.num_edges_coo
 
     def transposed(self):
         """The graph of ``torch.flip(edge_index, dims=[0])``: same structures, roles swapped."""
@@ -257,9 +263,23 @@ def _flipped_signature(edge_index, num_nodes):
             int(((s * 31 + d * 17) * w).sum().item()), str(edge_index.device))
 
 
-def get_graph(edge_index, num_nodes):
+def get_graph(edge_index, num_nodes, keep_self_loops=False):
     """RelationGraph for a COO edge_index; built on first sight, then served from the cache.
-    The caller must not mutate ``edge_index`` in place afterwards (the reference never does)."""
+    The caller must not mutate ``edge_index`` in place afterwards (the reference never does).
+    GCNConv / GATConv drop self-loop edges and add exactly one loop per node themselves; SAGEConv
+    keeps such edges as ordinary ones (``keep_self_loops=True``)."""
+    if keep_self_loops:
+        g = get_graph(edge_index, num_nodes)
+        if g.has_no_self_loops:
+            return g
+        key = ('keep', edge_index.data_ptr(), int(edge_index.shape[1]), num_nodes, str(edge_index.device))
+        hit = _by_ptr.get(key)
+        if hit is not None and hit[0]() is not None:
+            return hit[1]
+        import weakref
+        gk = RelationGraph.from_edge_index(edge_index, num_nodes, drop_self_loops=False)
+        _by_ptr[key] = (weakref.ref(edge_index), gk)
+        return gk
     if not edge_index.is_cuda:
         raise RuntimeError('graph_recsys_benchmark_b200 runs on CUDA only (sm_100a); got a %s edge_index'
                            % edge_index.device)

@@ -75,7 +75,7 @@ class PEABaseChannel(torch.nn.Module):
             layer = self.gnn_layers[step_idx]
             ei = edge_index_list[step_idx]
             relu = step_idx < self.num_steps - 1
-            g = get_graph(ei, n)
+            g = get_graph(ei, n, keep_self_loops=getattr(layer, 'keeps_self_loops', False))
             kw = {}
             if step_idx == 0 and shared is not None and getattr(layer, 'shares_aggregate', None):
                 key = (layer.shares_aggregate, id(g))

@@ -8,6 +8,7 @@ from .base import PEABaseChannel, PEABaseRecsysModel
 
 class _SageLayer(PEASageConv):
     shares_aggregate = 'sage'
+    keeps_self_loops = True
 
     @staticmethod
     def aggregate_input(x, g):

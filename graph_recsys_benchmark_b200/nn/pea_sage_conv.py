@@ -24,7 +24,7 @@ class PEASageConv(torch.nn.Module):
         self.lin_root.reset_parameters()
 
     def forward(self, x, edge_index, relu=False, graph=None, aggregated=None):
-        g = graph if graph is not None else get_graph(edge_index, x.size(0))
+        g = graph if graph is not None else get_graph(edge_index, x.size(0), keep_self_loops=True)
         if self.in_channels <= self.out_channels:
             m = aggregated if aggregated is not None else F_.sage_mean_aggregate(x, g)
             rel = F_.linear(m, self.lin_rel.weight, self.lin_rel.bias, w_is_out_in=True)

@@ -88,6 +88,9 @@ class BaseSolver(object):
 
     def _batches(self, dataset):
         """Index batches in torch.utils.data.DataLoader(shuffle=True) order (solvers.py:195-200)."""
+        # DataLoader.__iter__ draws its worker base seed from the global torch generator before the
+        # sampler draws the permutation seed; consume it too so the permutation is the same one.
+        torch.empty((), dtype=torch.int64).random_()
         sampler = BatchSampler(RandomSampler(dataset), batch_size=self.train_args['batch_size'], drop_last=False)
         for indices in sampler:
             yield dataset.get_batch(indices) if hasattr(dataset, 'get_batch') else \

@@ -37,6 +37,8 @@ typedef void* peagnn_stream_t; /* cudaStream_t */
 
 int peagnn_version(void);
 const char* peagnn_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+unsigned long long peagnn_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Graph preparation (integer, bit-exact).

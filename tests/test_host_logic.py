@@ -1,0 +1,175 @@
+"""CPU: host-side logic of the drop-in layer - dataset schema, metapath tables, negative sampling
+and candidate draws (bit-exact against the oracle's loop-for-loop restatement of the reference),
+checkpoint key compatibility against the shipped checkpoints' schema (tests/golden)."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import model_kwargs, oracle_model_for, product_model_for
+from oracle import graph as ograph, sampling as osampling, solver as osolver
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+@pytest.fixture(scope='module')
+def tiny():
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+    return SyntheticHIN('tiny', seed=7)
+
+
+def test_synthetic_schema(tiny):
+    ds = tiny
+    assert ds.num_nodes == sum(ds.num_nodes_dict.values()) == 227
+    accs = [ds.type_accs[t] for t in ds.types]
+    assert accs == sorted(accs) and accs[0] == 0                      # ids contiguous by type, users first
+    u2i = ds.edge_index_nps['user2item']
+    assert u2i.dtype == np.float64 and u2i.shape[0] == 2              # float64 upstream (movielens.py:294)
+    assert (np.diff(u2i[0]) >= 0).all()                               # grouped by user
+    i0 = ds.type_accs['iid']
+    for name, ei in ds.edge_index_nps.items():
+        src_t, dst_t = name.split('2')
+        lo = ds.type_accs['iid' if dst_t == 'item' else 'uid']
+        n = ds.num_iids if dst_t == 'item' else ds.num_uids
+        assert ((ei[1] >= lo) & (ei[1] < lo + n)).all(), name
+    # duplicates are kept in the tagging relations
+    t2i = ds.edge_index_nps['tag2item']
+    assert t2i.shape[1] == 150
+    for u in range(ds.num_uids):
+        pos, neg = ds.test_pos_unid_inid_map[u], ds.neg_unid_inid_map[u]
+        assert len(pos) == 1 and pos[0] not in neg
+        seen = set(u2i[1][u2i[0] == u].astype(int).tolist())
+        assert not (seen & set(neg)) and pos[0] not in seen
+        assert len(seen) + 1 + len(neg) == ds.num_iids
+    assert ds['num_nodes'] == ds.num_nodes and ds['nope'] is None     # dataset['attr'] access (movielens.py:1141)
+    assert len(ds.iid_feat_nids) == ds.num_iids and len(ds.uid_feat_nids) == ds.num_uids
+    assert ds.nid2e_dict[i0][0] == 'iid' and ds.nid2e_dict[ds.type_accs['tid'] + 3] == ('tid', 3)
+
+
+def test_synthetic_is_deterministic():
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+    a, b, c = SyntheticHIN('tiny', seed=3), SyntheticHIN('tiny', seed=3), SyntheticHIN('tiny', seed=4)
+    for k in a.edge_index_nps:
+        assert np.array_equal(a.edge_index_nps[k], b.edge_index_nps[k])
+    assert not np.array_equal(a.edge_index_nps['user2item'], c.edge_index_nps['user2item'])
+
+
+def test_lazy_neg_map_matches_dense():
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+    a, b = SyntheticHIN('tiny', seed=3), SyntheticHIN('tiny', seed=3, dense_neg_map=False)
+    for u in (0, 5, 39):
+        assert a.neg_unid_inid_map[u] == b.neg_unid_inid_map[u].tolist()
+
+
+@pytest.mark.parametrize('dataset,name,P', [('Movielens', 'latest-small', 9), ('Movielens', '25m', 13), ('Yelp', None, 11)])
+def test_metapath_tables_match_oracle(dataset, name, P):
+    from graph_recsys_benchmark_b200.utils import metapath_table
+    prod = metapath_table({'dataset': dataset, 'name': name})
+    ora = ograph.metapath_tables(dataset, name)
+    assert len(prod) == P
+    assert [[(r, int(f)) for r, f in path] for path in prod] == [[(r, int(f)) for r, f in path] for path in ora]
+
+
+def test_update_pea_graph_input_matches_oracle(tiny):
+    from graph_recsys_benchmark_b200.utils import update_pea_graph_input
+    prod = update_pea_graph_input({'dataset': 'Movielens', 'name': 'latest-small'}, {'device': 'cpu'}, tiny)
+    ora = ograph.metapath_edge_index_list(tiny, 'Movielens', 'latest-small')
+    assert len(prod) == len(ora) == 9
+    for p, o in zip(prod, ora):
+        assert len(p) == len(o) == 2
+        for a, b in zip(p, o):
+            assert a.dtype == torch.long and torch.equal(a, b)
+    assert prod[0][0] is prod[1][1]          # the same relation tensor is reused, as upstream
+
+
+@pytest.mark.parametrize('strategy', ['unseen', 'random'])
+@pytest.mark.parametrize('entity_aware', [False, True])
+def test_negative_sampling_bit_exact(tiny, strategy, entity_aware):
+    ds = tiny
+    ds.sampling_strategy, ds.entity_aware = strategy, entity_aware
+    osolver.seed_everything(1)
+    ds.cf_negative_sampling()
+    got = ds.get_batch(list(range(64)))
+    state = (random.getstate(), np.random.get_state()[1].copy(), torch.get_rng_state())
+    osolver.seed_everything(1)
+    train = osampling.cf_negative_sampling_bpr(ds, ds.num_negative_samples, strategy)
+    want = torch.stack([osampling.getitem(ds, train, i, entity_aware) for i in range(64)])
+    assert torch.equal(ds.train_data, train) and torch.equal(got, want)
+    assert got.shape == (64, 9 if entity_aware else 3) and got.dtype == torch.long
+    # the three generators end in the same state -> later draws stay aligned too
+    assert random.getstate() == state[0] and np.array_equal(np.random.get_state()[1], state[1])
+    assert torch.equal(torch.get_rng_state(), state[2])
+    ds.sampling_strategy, ds.entity_aware = 'unseen', False
+
+
+def test_candidates_bit_exact(tiny):
+    from graph_recsys_benchmark_b200.solvers import BaseSolver
+    s = BaseSolver(None, {}, {}, {'device': 'cpu', 'num_neg_candidates': 99})
+    np.random.seed(2020)
+    users, cand, n_pos = s.generate_all_candidates(tiny)
+    end_state = np.random.get_state()[1].copy()
+    np.random.seed(2020)
+    for k, u in enumerate(tiny.test_pos_unid_inid_map.keys()):
+        pos, neg = osolver.generate_candidates(tiny, u, 99)
+        assert users[k] == u and cand[k, :n_pos].tolist() == pos and cand[k, n_pos:].tolist() == [int(v) for v in neg]
+    assert np.array_equal(np.random.get_state()[1], end_state)
+    np.random.seed(2020)
+    pos, neg = s.generate_candidates(tiny, 3)        # the per-user API draws the same stream
+    assert pos == tiny.test_pos_unid_inid_map[3] and len(neg) == 99
+
+
+def test_batches_follow_dataloader_order(tiny):
+    from torch.utils.data import DataLoader
+    from graph_recsys_benchmark_b200.solvers import BaseSolver
+    osolver.seed_everything(1)
+    tiny.cf_negative_sampling()
+    s = BaseSolver(None, {}, {}, {'device': 'cpu', 'batch_size': 100})
+    torch.manual_seed(5)
+    got = list(s._batches(tiny))
+    torch.manual_seed(5)
+    want = list(DataLoader(tiny, shuffle=True, batch_size=100, num_workers=0))
+    assert len(got) == len(want) and all(torch.equal(a, b) for a, b in zip(got, want))
+
+
+def test_state_dict_matches_shipped_checkpoints():
+    """Key names + shapes of the reference's trained checkpoints (golden schema) load into the
+    drop-in models built on an N = 2933 graph, including the legacy mpagcn_* naming."""
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+    from graph_recsys_benchmark_b200.utils import remap_legacy_state_dict
+    schema = json.load(open(os.path.join(GOLDEN, 'checkpoint_schema.json')))
+    assert len(schema) == 6
+    ds = SyntheticHIN('ml-small-ref', seed=1)
+    assert ds.num_nodes == 2933 and ds.num_uids == 608
+    for key, entry in schema.items():
+        kind = {'PEAGCN': 'gcn', 'PEAGAT': 'gat', 'PEASage': 'sage'}[key.split('/')[0]]
+        model = product_model_for(ds, kind, device='cpu')
+        fake = remap_legacy_state_dict({k: torch.zeros(shape) for k, shape in entry['state_dict'].items()})
+        mine = {k: list(v.shape) for k, v in model.state_dict().items()}
+        assert mine == {k: list(v.shape) for k, v in fake.items()}, key
+        model.load_state_dict(fake)
+        assert entry['adam']['lr'] == 1e-3 and entry['adam']['step'] == 9270 and entry['epoch'] == 30
+
+
+def test_init_draw_order_matches_oracle(tiny):
+    """Same torch seed -> same initial parameters as the oracle model (which follows the reference's
+    constructor order: conv ctor, channel reset, model reset; base.py:181-189, peagcn.py:23)."""
+    for kind in ('gcn', 'gat', 'sage'):
+        torch.manual_seed(2020)
+        o = oracle_model_for(tiny, kind)
+        torch.manual_seed(2020)
+        m = product_model_for(tiny, kind, device='cpu')
+        for (k, a), (_, b) in zip(o.state_dict().items(), m.state_dict().items()):
+            assert torch.equal(a, b), (kind, k)
+
+
+def test_unsupported_options_raise(tiny):
+    kw = model_kwargs(tiny, 'gcn')
+    kw['if_use_features'] = True
+    from graph_recsys_benchmark_b200 import models
+    with pytest.raises(NotImplementedError):
+        product_model_for(tiny, 'gcn', device='cpu', channel_aggr='att').__class__(**kw)
+    with pytest.raises(AssertionError):
+        product_model_for(tiny, 'gcn', device='cpu', steps=[2] * 8)
