@@ -43,6 +43,11 @@ __device__ __forceinline__ float4 ldg4(const float* p) {
 }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// offset of row c in a table with leading dimension ld: one IMAD.WIDE.U32 instead of a 64x64 multiply
+__device__ __forceinline__ size_t row_off(int c, unsigned ld) {
+  return (size_t)((unsigned long long)(unsigned)c * (unsigned long long)ld);
+}
+
 __device__ __forceinline__ float leaky(float s, float slope) { return s > 0.f ? s : slope * s; }
 
 // -log(sigmoid(z)) evaluated the way the reference does it (sigmoid().log(), models/base.py:48):

@@ -1,6 +1,6 @@
 // K3: GAT edge-softmax aggregation and its backward (GATConv of PyG-1.5.0 as called from
 // models/peagat.py:16-21).  All four passes run on the shared CSR traversal
-// engine (csr_traverse.cuh): one G-lane group per (destination row, head).
+// engine (csr_traverse.cuh): one warp per (destination row, head).
 //
 //   e_ij   = leaky_relu(a_i[i] + a_j[j], slope)          j over row i's neighbours plus i itself
 //   alpha  = exp(e_ij - max_i) / (sum_i exp(e - max_i) + 1e-16)
@@ -11,7 +11,7 @@
 
 namespace peagnn {
 
-// ---- pass 1: row max ------------------------------------------------------------------------
+// ---- pass 1: row max (G = 1: 32 edges per warp instruction) -----------------------------------
 struct RowMaxOp {
   static constexpr int NV = 1;
   static constexpr bool kMax = true;
@@ -24,7 +24,7 @@ struct RowMaxOp {
   int row_offset;
   int h_;
 
-  __device__ __forceinline__ void row_begin(int, int h, int, unsigned) { h_ = h; }
+  __device__ __forceinline__ void row_begin(int, int h, int) { h_ = h; }
   __device__ __forceinline__ Edge load_edge(int, int c) const {
     Edge e;
     e.c = c;
@@ -32,13 +32,13 @@ struct RowMaxOp {
     e.w2 = 0.f;
     return e;
   }
-  __device__ __forceinline__ void apply(float* acc, int, int, float w, float, int, unsigned) const {
-    acc[0] = fmaxf(acc[0], w);
+  __device__ __forceinline__ void apply(float* acc, int, int, float w, float, int, bool valid) const {
+    if (valid) acc[0] = fmaxf(acc[0], w);
   }
-  __device__ __forceinline__ void finish(float* acc, int i, int h, int gl, unsigned) const {
+  __device__ __forceinline__ void finish(float* acc, int i, int h, int, bool writer) const {
     const int64_t gi = (int64_t)(row_offset + i) * heads + h;
     const float m = fmaxf(acc[0], __ldg(a_j + gi));  // the self loop
-    if (gl == 0) rowmax[gi] = leaky(__ldg(a_i + gi) + m, slope);
+    if (writer) rowmax[gi] = leaky(__ldg(a_i + gi) + m, slope);
   }
 };
 
@@ -65,7 +65,7 @@ struct GatAggOp {
   float ai_, m_;
   int h_;
 
-  __device__ __forceinline__ void row_begin(int i, int h, int, unsigned) {
+  __device__ __forceinline__ void row_begin(int i, int h, int) {
     const int64_t gi = (int64_t)(row_offset + i) * heads + h;
     ai_ = __ldg(a_i + gi);
     m_ = __ldg(rowmax + gi);
@@ -78,12 +78,12 @@ struct GatAggOp {
     e.w2 = 0.f;
     return e;
   }
-  __device__ __forceinline__ void apply(float* acc, int, int c, float w, float, int gl, unsigned) const {
-    const float* xr = H + (int64_t)c * ldh + (int64_t)h_ * feat;
+  __device__ __forceinline__ void apply(float* acc, int, int c, float w, float, int gl, bool valid) const {
+    const float* xr = H + row_off(c, (unsigned)ldh) + h_ * feat;
 #pragma unroll
     for (int ch = 0; ch < CPL; ++ch) {
       const int idx = gl + ch * G;
-      if (idx < f4) {
+      if (valid && idx < f4) {
         const float4 v = ldg4(xr + 4 * idx);
         acc[4 * ch + 0] = fmaf(w, v.x, acc[4 * ch + 0]);
         acc[4 * ch + 1] = fmaf(w, v.y, acc[4 * ch + 1]);
@@ -91,9 +91,10 @@ struct GatAggOp {
         acc[4 * ch + 3] = fmaf(w, v.w, acc[4 * ch + 3]);
       }
     }
-    acc[4 * CPL] += w;
+    if (valid) acc[4 * CPL] += w;
   }
-  __device__ __forceinline__ void finish(float* acc, int i, int h, int gl, unsigned) const {
+  __device__ __forceinline__ void finish(float* acc, int i, int h, int gl, bool writer) const {
+    if (!writer) return;
     const int64_t gi = (int64_t)(row_offset + i) * heads + h;
     const float ws = expf(leaky(ai_ + __ldg(a_j + gi), slope) - m_);  // self loop, appended last
     const float den = acc[4 * CPL] + ws + 1e-16f;
@@ -155,7 +156,7 @@ struct GatBwdDstOp {
   int h_;
   float4 g_[CPL];
 
-  __device__ __forceinline__ void row_begin(int i, int h, int gl, unsigned gmask) {
+  __device__ __forceinline__ void row_begin(int i, int h, int gl) {
     const int64_t gi = (int64_t)(row_offset + i) * heads + h;
     ai_ = __ldg(a_i + gi);
     m_ = __ldg(rowmax + gi);
@@ -178,7 +179,7 @@ struct GatBwdDstOp {
         d += g_[ch].x * a.x + g_[ch].y * a.y + g_[ch].z * a.z + g_[ch].w * a.w;
       }
     }
-    D_ = group_sum<G>(d, gmask);
+    D_ = group_sum<G>(d);
   }
   __device__ __forceinline__ Edge load_edge(int, int c) const {
     Edge e;
@@ -187,8 +188,9 @@ struct GatBwdDstOp {
     e.w2 = 0.f;
     return e;
   }
-  __device__ __forceinline__ float edge_terms(int64_t node, float s_raw, int gl, unsigned gmask, float& alpha) const {
-    const float* xr = H + node * ldh + (int64_t)h_ * feat;
+  // executed by every lane of the warp (shuffles inside)
+  __device__ __forceinline__ float edge_terms(int64_t node, float s_raw, int gl, float& alpha) const {
+    const float* xr = H + row_off((int)node, (unsigned)ldh) + h_ * feat;
     float d = 0.f;
 #pragma unroll
     for (int ch = 0; ch < CPL; ++ch) {
@@ -198,26 +200,28 @@ struct GatBwdDstOp {
         d += g_[ch].x * v.x + g_[ch].y * v.y + g_[ch].z * v.z + g_[ch].w * v.w;
       }
     }
-    d = group_sum<G>(d, gmask);
+    d = group_sum<G>(d);
     alpha = expf(leaky(s_raw, slope) - m_) * inv_den_;
     const float de = alpha * (d - D_);
     return de * (s_raw > 0.f ? 1.f : slope);
   }
-  __device__ __forceinline__ void apply(float* acc, int e, int c, float s_raw, float, int gl, unsigned gmask) const {
+  __device__ __forceinline__ void apply(float* acc, int e, int c, float s_raw, float, int gl, bool valid) const {
     float alpha;
-    const float ds = edge_terms((int64_t)c, s_raw, gl, gmask, alpha);
-    if (gl == 0) {
-      alpha_e[(int64_t)e * heads + h_] = alpha;
-      ds_e[(int64_t)e * heads + h_] = ds;
+    const float ds = edge_terms((int64_t)c, s_raw, gl, alpha);
+    if (valid) {
+      if (gl == 0) {
+        alpha_e[(int64_t)e * heads + h_] = alpha;
+        ds_e[(int64_t)e * heads + h_] = ds;
+      }
+      acc[0] += ds;
     }
-    acc[0] += ds;
   }
-  __device__ __forceinline__ void finish(float* acc, int i, int h, int gl, unsigned gmask) const {
+  __device__ __forceinline__ void finish(float* acc, int i, int h, int gl, bool writer) const {
     const int64_t node = row_offset + i;
     const int64_t gi = node * heads + h;
     float alpha;
-    const float ds = edge_terms(node, ai_ + __ldg(a_j + gi), gl, gmask, alpha);
-    if (gl == 0) {
+    const float ds = edge_terms(node, ai_ + __ldg(a_j + gi), gl, alpha);
+    if (writer && gl == 0) {
       alpha_self[gi] = alpha;
       ds_self[gi] = ds;
       d_ai[gi] = acc[0] + ds;
@@ -246,7 +250,7 @@ struct GatBwdSrcOp {
   int row_offset;
   int h_;
 
-  __device__ __forceinline__ void row_begin(int, int h, int, unsigned) { h_ = h; }
+  __device__ __forceinline__ void row_begin(int, int h, int) { h_ = h; }
   __device__ __forceinline__ Edge load_edge(int e, int c) const {
     const int64_t p = (int64_t)__ldg(perm + e) * heads + h_;
     Edge r;
@@ -255,12 +259,12 @@ struct GatBwdSrcOp {
     r.w2 = __ldg(ds_e + p);
     return r;
   }
-  __device__ __forceinline__ void apply(float* acc, int, int c, float w, float w2, int gl, unsigned) const {
-    const float* xr = dout + (int64_t)c * ldd + (int64_t)h_ * feat;
+  __device__ __forceinline__ void apply(float* acc, int, int c, float w, float w2, int gl, bool valid) const {
+    const float* xr = dout + row_off(c, (unsigned)ldd) + h_ * feat;
 #pragma unroll
     for (int ch = 0; ch < CPL; ++ch) {
       const int idx = gl + ch * G;
-      if (idx < f4) {
+      if (valid && idx < f4) {
         const float4 v = ldg4(xr + 4 * idx);
         acc[4 * ch + 0] = fmaf(w, v.x, acc[4 * ch + 0]);
         acc[4 * ch + 1] = fmaf(w, v.y, acc[4 * ch + 1]);
@@ -268,9 +272,10 @@ struct GatBwdSrcOp {
         acc[4 * ch + 3] = fmaf(w, v.w, acc[4 * ch + 3]);
       }
     }
-    acc[4 * CPL] += w2;
+    if (valid) acc[4 * CPL] += w2;
   }
-  __device__ __forceinline__ void finish(float* acc, int i, int h, int gl, unsigned) const {
+  __device__ __forceinline__ void finish(float* acc, int i, int h, int gl, bool writer) const {
+    if (!writer) return;
     const int64_t node = row_offset + i;
     const int64_t gi = node * heads + h;
     const float ws = __ldg(alpha_self + gi);
@@ -306,11 +311,11 @@ using namespace peagnn;
 #define PEAGNN_GEOM_DISPATCH(feat_, CALL)             \
   do {                                                \
     const Geometry ge__ = geometry_for(feat_);        \
-    if (ge__.G == 4) { CALL(1, 4, 2); }               \
-    else if (ge__.G == 8) { CALL(1, 8, 1); }          \
-    else if (ge__.G == 16) { CALL(1, 16, 1); }        \
-    else if (ge__.CPL == 1) { CALL(1, 32, 1); }       \
-    else { CALL(2, 32, 1); }                          \
+    if (ge__.G == 4) { CALL(1, 4); }                  \
+    else if (ge__.G == 8) { CALL(1, 8); }             \
+    else if (ge__.G == 16) { CALL(1, 16); }           \
+    else if (ge__.CPL == 1) { CALL(1, 32); }          \
+    else { CALL(2, 32); }                             \
   } while (0)
 
 extern "C" int peagnn_gat_rowmax(const peagnn_csr_t* g, const float* a_i, const float* a_j, int32_t heads,
@@ -323,7 +328,7 @@ extern "C" int peagnn_gat_rowmax(const peagnn_csr_t* g, const float* a_i, const 
   RowMaxOp op;
   op.heads = heads; op.a_i = a_i; op.a_j = a_j; op.rowmax = rowmax; op.slope = slope;
   op.row_offset = g->row_offset; op.h_ = 0;
-  return launch_csr<RowMaxOp, 8, 1>(*g, op, stream, "peagnn_gat_rowmax");
+  return launch_csr<RowMaxOp, 1>(*g, op, stream, "peagnn_gat_rowmax");
 }
 
 extern "C" int peagnn_gat_aggregate(const peagnn_csr_t* g, const float* H, int64_t ldh, int32_t feat,
@@ -336,14 +341,14 @@ extern "C" int peagnn_gat_aggregate(const peagnn_csr_t* g, const float* H, int64
   PEAGNN_REQUIRE(H && a_i && a_j && rowmax && out && ldh % 4 == 0 && ldo % 4 == 0 && aligned16(H) && aligned16(out) && (!bias || aligned16(bias)),
                  "peagnn_gat_aggregate: bad pointers / alignment");
   if (g->nrows == 0) return PEAGNN_OK;
-#define CALL(CPL_, G_, IPL_)                                                                     \
+#define CALL(CPL_, G_)                                                                           \
   {                                                                                              \
     GatAggOp<CPL_, G_> op;                                                                       \
     op.heads = heads; op.H = H; op.ldh = ldh; op.feat = feat; op.f4 = feat / 4; op.a_i = a_i;    \
     op.a_j = a_j; op.rowmax = rowmax; op.denom = denom; op.out = out; op.ldo = ldo;              \
     op.bias = bias; op.slope = slope; op.row_offset = g->row_offset; op.relu = relu;             \
     op.ai_ = 0.f; op.m_ = 0.f; op.h_ = 0;                                                        \
-    return launch_csr<GatAggOp<CPL_, G_>, G_, IPL_>(*g, op, stream, "peagnn_gat_aggregate");     \
+    return launch_csr<GatAggOp<CPL_, G_>, G_>(*g, op, stream, "peagnn_gat_aggregate");           \
   }
   PEAGNN_GEOM_DISPATCH(feat, CALL);
 #undef CALL
@@ -353,9 +358,9 @@ extern "C" int peagnn_gat_aggregate(const peagnn_csr_t* g, const float* H, int64
 extern "C" int peagnn_gat_backward_dst(const peagnn_csr_t* g, const float* H, int64_t ldh, int32_t feat,
                                        int32_t heads, const float* a_i, const float* a_j, float slope,
                                        const float* rowmax, const float* denom, const float* agg,
-                                       int64_t lda, const float* agg_bias, const float* dout, int64_t ldd, float* alpha_e,
-                                       float* ds_e, float* alpha_self, float* ds_self, float* d_ai,
-                                       peagnn_stream_t stream_) {
+                                       int64_t lda, const float* agg_bias, const float* dout, int64_t ldd,
+                                       float* alpha_e, float* ds_e, float* alpha_self, float* ds_self,
+                                       float* d_ai, peagnn_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_gat_common(g, feat, heads, "peagnn_gat_backward_dst");
   if (rc) return rc;
@@ -364,16 +369,16 @@ extern "C" int peagnn_gat_backward_dst(const peagnn_csr_t* g, const float* H, in
   PEAGNN_REQUIRE(ldh % 4 == 0 && lda % 4 == 0 && ldd % 4 == 0 && aligned16(H) && aligned16(agg) && aligned16(dout),
                  "peagnn_gat_backward_dst: alignment");
   if (g->nrows == 0) return PEAGNN_OK;
-#define CALL(CPL_, G_, IPL_)                                                                       \
+#define CALL(CPL_, G_)                                                                             \
   {                                                                                                \
     GatBwdDstOp<CPL_, G_> op;                                                                      \
     op.heads = heads; op.H = H; op.ldh = ldh; op.feat = feat; op.f4 = feat / 4; op.a_i = a_i;      \
-    op.a_j = a_j; op.rowmax = rowmax; op.denom = denom; op.agg = agg; op.lda = lda; op.agg_bias = agg_bias; \
-    op.dout = dout; op.ldd = ldd; op.alpha_e = alpha_e; op.ds_e = ds_e;                            \
+    op.a_j = a_j; op.rowmax = rowmax; op.denom = denom; op.agg = agg; op.lda = lda;                \
+    op.agg_bias = agg_bias; op.dout = dout; op.ldd = ldd; op.alpha_e = alpha_e; op.ds_e = ds_e;    \
     op.alpha_self = alpha_self; op.ds_self = ds_self; op.d_ai = d_ai; op.slope = slope;            \
     op.row_offset = g->row_offset; op.ai_ = op.m_ = op.inv_den_ = op.D_ = 0.f; op.h_ = 0;          \
     for (int q = 0; q < CPL_; ++q) op.g_[q] = make_float4(0.f, 0.f, 0.f, 0.f);                     \
-    return launch_csr<GatBwdDstOp<CPL_, G_>, G_, IPL_>(*g, op, stream, "peagnn_gat_backward_dst"); \
+    return launch_csr<GatBwdDstOp<CPL_, G_>, G_>(*g, op, stream, "peagnn_gat_backward_dst");       \
   }
   PEAGNN_GEOM_DISPATCH(feat, CALL);
 #undef CALL
@@ -390,14 +395,14 @@ extern "C" int peagnn_gat_backward_src(const peagnn_csr_t* gt, const int32_t* pe
   PEAGNN_REQUIRE(alpha_self && ds_self && dout && dH && d_aj, "peagnn_gat_backward_src: null pointer");
   PEAGNN_REQUIRE(ldh % 4 == 0 && ldd % 4 == 0 && aligned16(dH) && aligned16(dout), "peagnn_gat_backward_src: alignment");
   if (gt->nrows == 0) return PEAGNN_OK;
-#define CALL(CPL_, G_, IPL_)                                                                        \
+#define CALL(CPL_, G_)                                                                              \
   {                                                                                                 \
     GatBwdSrcOp<CPL_, G_> op;                                                                       \
     op.heads = heads; op.perm = perm; op.alpha_e = alpha_e; op.ds_e = ds_e;                         \
     op.alpha_self = alpha_self; op.ds_self = ds_self; op.dout = dout; op.ldd = ldd;                 \
     op.feat = feat; op.f4 = feat / 4; op.dH = dH; op.ldh = ldh; op.d_aj = d_aj;                     \
     op.row_offset = gt->row_offset; op.h_ = 0;                                                      \
-    return launch_csr<GatBwdSrcOp<CPL_, G_>, G_, IPL_>(*gt, op, stream, "peagnn_gat_backward_src"); \
+    return launch_csr<GatBwdSrcOp<CPL_, G_>, G_>(*gt, op, stream, "peagnn_gat_backward_src");       \
   }
   PEAGNN_GEOM_DISPATCH(feat, CALL);
 #undef CALL

@@ -22,7 +22,7 @@ struct SpmmOp {
   int row_offset;
   int self_loop, relu, accumulate;
 
-  __device__ __forceinline__ void row_begin(int, int, int, unsigned) {}
+  __device__ __forceinline__ void row_begin(int, int, int) {}
 
   __device__ __forceinline__ Edge load_edge(int, int c) const {
     Edge e;
@@ -32,12 +32,12 @@ struct SpmmOp {
     return e;
   }
 
-  __device__ __forceinline__ void apply(float* acc, int, int c, float w, float, int gl, unsigned) const {
-    const float* xr = X + (int64_t)c * ldx;
+  __device__ __forceinline__ void apply(float* acc, int, int c, float w, float, int gl, bool valid) const {
+    const float* xr = X + row_off(c, (unsigned)ldx);
 #pragma unroll
     for (int ch = 0; ch < CPL; ++ch) {
       const int idx = gl + ch * G;
-      if (idx < f4) {
+      if (valid && idx < f4) {
         const float4 v = ldg4(xr + 4 * idx);
         acc[4 * ch + 0] = fmaf(w, v.x, acc[4 * ch + 0]);
         acc[4 * ch + 1] = fmaf(w, v.y, acc[4 * ch + 1]);
@@ -47,7 +47,8 @@ struct SpmmOp {
     }
   }
 
-  __device__ __forceinline__ void finish(float* acc, int i, int, int gl, unsigned) const {
+  __device__ __forceinline__ void finish(float* acc, int i, int, int gl, bool writer) const {
+    if (!writer) return;
     const int gi = row_offset + i;
     const float r = rs ? __ldg(rs + gi) : 1.f;
     const float sw = self_loop ? (cs ? __ldg(cs + gi) : 1.f) : 0.f;
@@ -70,12 +71,12 @@ struct SpmmOp {
           const float4 b = ldg4(bias + 4 * idx);
           a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         }
-        if (relu) {
-          a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
-        }
         if (accumulate) {
           const float4 p = *reinterpret_cast<const float4*>(o + 4 * idx);
           a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+        }
+        if (relu) {
+          a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
         }
         st4(o + 4 * idx, a);
       }
@@ -83,7 +84,7 @@ struct SpmmOp {
   }
 };
 
-template <int CPL, int G, int IPL>
+template <int CPL, int G>
 static int run_spmm(const peagnn_csr_t& g, const float* X, int64_t ldx, int feat, float* out,
                     int64_t ldo, const float* rs, const float* cs, int self_loop, const float* bias,
                     int relu, int accumulate, cudaStream_t stream) {
@@ -92,7 +93,7 @@ static int run_spmm(const peagnn_csr_t& g, const float* X, int64_t ldx, int feat
   op.X = X; op.ldx = ldx; op.f4 = feat / 4; op.out = out; op.ldo = ldo;
   op.rs = rs; op.cs = cs; op.bias = bias; op.row_offset = g.row_offset;
   op.self_loop = self_loop; op.relu = relu; op.accumulate = accumulate;
-  return launch_csr<SpmmOp<CPL, G>, G, IPL>(g, op, stream, "peagnn_spmm");
+  return launch_csr<SpmmOp<CPL, G>, G>(g, op, stream, "peagnn_spmm");
 }
 
 }  // namespace peagnn
@@ -116,13 +117,13 @@ extern "C" int peagnn_spmm(const peagnn_csr_t* g, const float* X, int64_t ldx, i
   PEAGNN_REQUIRE(aligned16(X) && aligned16(out) && (!bias || aligned16(bias)), "peagnn_spmm: pointers must be 16-byte aligned");
   if (g->nrows == 0) return PEAGNN_OK;
   const Geometry ge = geometry_for(feat);
-#define PEAGNN_SPMM_CASE(CPL_, G_, IPL_) \
-  return run_spmm<CPL_, G_, IPL_>(*g, X, ldx, feat, out, ldo, rs, cs, self_loop, bias, relu, accumulate, stream)
-  if (ge.G == 4) PEAGNN_SPMM_CASE(1, 4, 2);
-  if (ge.G == 8) PEAGNN_SPMM_CASE(1, 8, 1);
-  if (ge.G == 16) PEAGNN_SPMM_CASE(1, 16, 1);
-  if (ge.CPL == 1) PEAGNN_SPMM_CASE(1, 32, 1);
-  if (ge.CPL == 2) PEAGNN_SPMM_CASE(2, 32, 1);
-  PEAGNN_SPMM_CASE(4, 32, 1);
+#define PEAGNN_SPMM_CASE(CPL_, G_) \
+  return run_spmm<CPL_, G_>(*g, X, ldx, feat, out, ldo, rs, cs, self_loop, bias, relu, accumulate, stream)
+  if (ge.G == 4) PEAGNN_SPMM_CASE(1, 4);
+  if (ge.G == 8) PEAGNN_SPMM_CASE(1, 8);
+  if (ge.G == 16) PEAGNN_SPMM_CASE(1, 16);
+  if (ge.CPL == 1) PEAGNN_SPMM_CASE(1, 32);
+  if (ge.CPL == 2) PEAGNN_SPMM_CASE(2, 32);
+  PEAGNN_SPMM_CASE(4, 32);
 #undef PEAGNN_SPMM_CASE
 }
