@@ -221,15 +221,16 @@ def run_product(args):
     host_batches = make_batches(ds, B, K + W, seed=100 + rank).pin_memory()
     dev_batches = host_batches.to(dev)
 
+    sharded = False
+    if world > 1 and args.model in ('gcn', 'sage'):
+        from graph_recsys_benchmark_b200.distributed import shard_model
+        shard_model(model, world, rank)
+        sharded = True
+
     def allreduce_grads():
         if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            off = 0
-            for p in params:
-                n = p.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p))
-                off += n
+            from graph_recsys_benchmark_b200.distributed import allreduce_gradients
+            allreduce_gradients(params)
 
     def step(batch):
         opt.zero_grad(set_to_none=True)
@@ -315,8 +316,11 @@ def run_product(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': dict(workload_config(args), num_nodes=ds.num_nodes,
                            edges_user2item=int(ds.edge_index_nps['user2item'].shape[1]),
-                           parallelism='dp%d (replicated propagation, NCCL allreduce of gradients)' % world
-                           if world > 1 else 'single GPU'),
+                           parallelism=('single GPU' if world == 1 else
+                                        ('%d-way destination-row sharded propagation (NCCL all-gather / reduce-scatter '
+                                         'per step) + data-parallel batches (NCCL all-reduce of gradients)' % world
+                                         if sharded else
+                                         'dp%d (replicated propagation, NCCL all-reduce of gradients)' % world))),
             'e2e': {'value': world * B * K / (ms_e2e * 1e-3), 'unit': 'triples/s', 'h2d_bytes_per_step': B * 3 * 8,
                     'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / K, 'last_loss': last},
             'gpu_launches': launches,

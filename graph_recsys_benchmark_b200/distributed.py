@@ -1,0 +1,329 @@
+"""1-D destination-row sharding of the metapath propagation across the GPUs of one box
+(BASELINE.json north_star).  The reference has no distributed code at all -
+this is the multi-GPU form of the same arithmetic:
+
+  * rank r of R owns the destination rows i with i % R == r (cyclic, so popular items / active
+    users / hot tags spread evenly; node ids are contiguous by type upstream, a blocked split
+    would put every item on one rank);
+  * an aggregation step computes only the owned rows; what the next step gathers from is
+    re-assembled with ONE NCCL all-gather per step (its backward is a reduce-scatter);
+  * gathered tables live in "rank-major" order: position pi(i) = (i % R) * rows_per_rank + i // R,
+    which is exactly what all_gather_into_tensor produces, so no re-shuffle is needed - the shard's
+    column indices are stored pre-permuted;
+  * self loops (GCN) are stored as explicit edges of the owning rank, so the transposed pass needs
+    no special case;
+  * BPR minibatches are data-parallel (each rank scores its own triples against the full fused
+    representation); parameter gradients - the embedding table's partial d_x included - are summed
+    with one all-reduce per step.
+One process per GPU; torch.distributed (NCCL over NVLink 5 / NVSwitch) owns the communicator.
+"""
+import torch
+import torch.distributed as dist
+
+from . import functional as F_
+from .graph import build_csr
+
+
+class ShardPlan(object):
+    def __init__(self, num_nodes, world_size, rank):
+        self.num_nodes, self.world, self.rank = int(num_nodes), int(world_size), int(rank)
+        self.rows_per_rank = (self.num_nodes + self.world - 1) // self.world
+        self.padded = self.rows_per_rank * self.world
+
+    def owner(self, ids):
+        return ids % self.world
+
+    def local_index(self, ids):
+        return ids // self.world
+
+    def to_rank_major(self, ids):
+        """pi(i): position of node i in an all-gathered (rank-major) table."""
+        return (ids % self.world) * self.rows_per_rank + ids // self.world
+
+    def local_global_ids(self, rank=None, device=None):
+        """Global ids of this rank's rows, padded with -1 up to rows_per_rank."""
+        r = self.rank if rank is None else rank
+        ids = torch.arange(self.rows_per_rank, device=device, dtype=torch.long) * self.world + r
+        return torch.where(ids < self.num_nodes, ids, torch.full_like(ids, -1))
+
+    def rank_major_to_global(self, device=None):
+        """[padded] global id stored at each rank-major position (-1 for padding)."""
+        return torch.cat([self.local_global_ids(r, device) for r in range(self.world)])
+
+
+def shard_coo(edge_index, plan, rank=None, explicit_self_loops=False, drop_self_loops=True):
+    """The edges a rank owns (target % R == rank), as (src_global, dst_local) int64 tensors.
+    With ``explicit_self_loops`` one loop per owned row is appended (GCNConv's add_remaining_self_loops
+    after dropping existing loops)."""
+    r = plan.rank if rank is None else rank
+    src, dst = edge_index[0], edge_index[1]
+    keep = (dst % plan.world) == r
+    if drop_self_loops:
+        keep &= src != dst
+    src, dst = src[keep], dst[keep]
+    if explicit_self_loops:
+        own = plan.local_global_ids(r, edge_index.device)
+        own = own[own >= 0]
+        src = torch.cat([src, own])
+        dst = torch.cat([dst, own])
+    return src, dst // plan.world
+
+
+class ShardedRelation(object):
+    """One rank's part of a relation, for one conv family ('gcn' or 'sage').
+
+    fwd(layout)  CSR over the owned rows gathering from a table in ``layout`` ('orig' = the
+                 embedding table / any [N, F] tensor in node-id order, 'rm' = an all-gathered
+                 rank-major table);
+    bwd(layout)  its transpose: rows = the table's rows, gathering from the local [rows_per_rank, F]
+                 gradient."""
+
+    def __init__(self, edge_index, plan, kind):
+        self.plan, self.kind = plan, kind
+        dev = edge_index.device
+        n = plan.num_nodes
+        src, dst = edge_index[0], edge_index[1]
+        nl = src != dst if kind == 'gcn' else torch.ones_like(src, dtype=torch.bool)
+        if kind == 'gcn':
+            deg = torch.bincount(src[nl], minlength=n).float() + 1.0       # source side + self loop
+            scale = deg.pow(-0.5)
+        else:
+            cnt = torch.bincount(dst, minlength=n).float()
+            scale = 1.0 / cnt.clamp(min=1.0)
+        own = plan.local_global_ids(device=dev)
+        valid = own >= 0
+        self.scale_orig = scale.contiguous()
+        rm_ids = plan.rank_major_to_global(dev)
+        self.scale_rm = torch.where(rm_ids >= 0, scale[rm_ids.clamp(min=0)], torch.zeros_like(rm_ids, dtype=scale.dtype)).contiguous()
+        self.scale_local = torch.where(valid, scale[own.clamp(min=0)], torch.zeros_like(own, dtype=scale.dtype)).contiguous()
+        self.src, self.dst_local = shard_coo(edge_index, plan, explicit_self_loops=(kind == 'gcn'),
+                                             drop_self_loops=(kind == 'gcn'))
+        self._fwd, self._bwd = {}, {}
+
+    def _cols(self, layout):
+        return self.src if layout == 'orig' else self.plan.to_rank_major(self.src)
+
+    def fwd(self, layout):
+        if layout not in self._fwd:
+            self._fwd[layout] = build_csr(self.dst_local, self._cols(layout), self.plan.rows_per_rank, False)
+        return self._fwd[layout]
+
+    def bwd(self, layout):
+        if layout not in self._bwd:
+            rows = self.plan.num_nodes if layout == 'orig' else self.plan.padded
+            self._bwd[layout] = build_csr(self._cols(layout), self.dst_local, rows, False)
+        return self._bwd[layout]
+
+    def table_scale(self, layout):
+        return self.scale_orig if layout == 'orig' else self.scale_rm
+
+
+class _ShardAggregate(torch.autograd.Function):
+    """Owned rows of  diag(rs) A diag(cs) X (+ bias)  over a ShardedRelation; X is a full table."""
+
+    @staticmethod
+    def forward(ctx, X, bias, rel, layout):
+        X = F_._rows(F_._req(X, 'table'))
+        feat = X.shape[1]
+        out = torch.empty(rel.plan.rows_per_rank, feat, dtype=torch.float32, device=X.device)
+        if rel.kind == 'gcn':
+            rs, cs = rel.scale_local, rel.table_scale(layout)
+        else:
+            rs, cs = rel.scale_local, None
+        F_.spmm_raw(rel.fwd(layout), X, feat, out, rs, cs, False, bias, False)
+        ctx.rel, ctx.layout, ctx.rows = rel, layout, X.shape[0]
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        rel, layout = ctx.rel, ctx.layout
+        dout = F_._rows(dout)
+        feat = dout.shape[1]
+        dX = db = None
+        if ctx.needs_input_grad[0]:
+            dX = torch.empty(ctx.rows, feat, dtype=torch.float32, device=dout.device)
+            if rel.kind == 'gcn':
+                rs, cs = rel.table_scale(layout), rel.scale_local
+            else:
+                rs, cs = None, rel.scale_local
+            F_.spmm_raw(rel.bwd(layout), dout, feat, dX, rs, cs, False)
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            # padding rows carry the bias too; their upstream gradient is zero by construction
+            db = torch.empty(feat, dtype=torch.float32, device=dout.device)
+            F_.wgrad_raw(None, dout, 0, feat, 0, None, db)
+        return dX, db, None, None
+
+
+def shard_aggregate(X, rel, layout, bias=None):
+    return _ShardAggregate.apply(X, bias, rel, layout)
+
+
+class _AllGatherRows(torch.autograd.Function):
+    """[rows_per_rank, F] per rank -> [R * rows_per_rank, F] rank-major on every rank.
+    Backward: every rank holds a gradient for the whole table; the owner needs their sum ->
+    reduce-scatter."""
+
+    @staticmethod
+    def forward(ctx, local, group):
+        local = local.contiguous()
+        world = dist.get_world_size(group)
+        out = torch.empty(world * local.shape[0], local.shape[1], dtype=local.dtype, device=local.device)
+        if dist.get_backend(group) == 'gloo':           # CPU / single-GPU test rigs
+            dist.all_gather(list(out.chunk(world, dim=0)), local, group=group)
+        else:
+            dist.all_gather_into_tensor(out, local, group=group)
+        ctx.group = group
+        return out
+
+    @staticmethod
+    def backward(ctx, dfull):
+        dfull = dfull.contiguous()
+        world = dist.get_world_size(ctx.group)
+        rows = dfull.shape[0] // world
+        if dist.get_backend(ctx.group) == 'gloo':       # gloo has no reduce-scatter: all-reduce, keep own slice
+            dfull = dfull.clone()
+            dist.all_reduce(dfull, op=dist.ReduceOp.SUM, group=ctx.group)
+            r = dist.get_rank(ctx.group)
+            return dfull[r * rows:(r + 1) * rows].contiguous(), None
+        dlocal = torch.empty(rows, dfull.shape[1], dtype=dfull.dtype, device=dfull.device)
+        dist.reduce_scatter_tensor(dlocal, dfull, op=dist.ReduceOp.SUM, group=ctx.group)
+        return dlocal, None
+
+
+def all_gather_rows(local, group=None):
+    return _AllGatherRows.apply(local, group)
+
+
+def allreduce_gradients(params, group=None):
+    """Sum the parameter gradients over ranks with one flat all-reduce (data-parallel BPR batches +
+    row-sharded propagation both leave per-rank partial sums)."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+class ShardedPropagation(object):
+    """Row-sharded forward of a PEAGCN / PEASage model (attached by ``shard_model``)."""
+
+    def __init__(self, model, plan, group=None):
+        self.model, self.plan, self.group = model, plan, group
+        self.kind = None
+        self._rels = {}
+        first = model.pea_channels[0].gnn_layers[0]
+        tag = getattr(first, 'shares_aggregate', None)
+        if tag not in ('gcn', 'sage'):
+            raise NotImplementedError('row-sharded propagation covers the GCN and SAGE families; PEAGAT runs '
+                                      'replicated propagation with data-parallel batches')
+        self.kind = tag
+        dev = model.x.device
+        own = plan.local_global_ids(device=dev)
+        self.own_ids = own.clamp(min=0)
+        self.own_valid = (own >= 0)
+        self.rm_of_global = plan.to_rank_major(torch.arange(plan.num_nodes, device=dev))
+
+    def relation(self, edge_index):
+        key = (edge_index.data_ptr(), int(edge_index.shape[1]))
+        hit = self._rels.get(key)
+        if hit is None:
+            for (_, e), (other, rel) in self._rels.items():
+                if e == edge_index.shape[1] and torch.equal(other, edge_index):
+                    hit = (edge_index, rel)
+                    break
+            if hit is None:
+                hit = (edge_index, ShardedRelation(edge_index, self.plan, self.kind))
+            self._rels[key] = hit
+        return hit[1]
+
+    def _local_rows(self, state):
+        layout, t = state
+        if layout == 'local':
+            return t
+        if layout == 'orig':
+            return t.index_select(0, self.own_ids)      # padding rows read node 0; never used downstream
+        raise AssertionError(layout)
+
+    def _table(self, state):
+        layout, t = state
+        if layout == 'local':
+            return 'rm', all_gather_rows(t, self.group)
+        return layout, t
+
+    def channel_outputs(self):
+        model = self.model
+        shared, pending = {}, []
+        for idx, channel in enumerate(model.pea_channels):
+            eil = model.meta_path_edge_index_list[idx]
+            assert len(eil) == channel.num_steps
+            state = ('orig', model.x)
+            result = None
+            for s, layer in enumerate(channel.gnn_layers):
+                rel = self.relation(eil[s])
+                last = s == channel.num_steps - 1
+                if layer.in_channels <= layer.out_channels:           # aggregate, then project
+                    layout, table = self._table(state)
+                    key = (id(rel), layout, id(table))
+                    if key not in shared:
+                        shared[key] = shard_aggregate(table, rel, layout)
+                    agg = shared[key]
+                    if self.kind == 'gcn':
+                        out = F_.linear(agg, layer.weight, layer.bias, w_is_out_in=False, relu=not last)
+                    else:
+                        relp = F_.linear(agg, layer.lin_rel.weight, layer.lin_rel.bias, w_is_out_in=True)
+                        out = F_.linear_accumulate(self._local_rows(state), layer.lin_root.weight, relp, relu=not last)
+                    state = ('local', out)
+                else:                                                  # project, then aggregate
+                    loc = self._local_rows(state)
+                    t = layer.project(loc)
+                    if last and model.batch_last_step:
+                        result = (layer, rel, t, loc)
+                        break
+                    table = all_gather_rows(t, self.group)
+                    agg = shard_aggregate(table, rel, 'rm', layer.post_bias())
+                    if self.kind == 'sage':
+                        agg = F_.linear_accumulate(loc, layer.lin_root.weight, agg, relu=not last)
+                    elif not last:
+                        raise NotImplementedError('relu after a narrowing GCN step inside a sharded channel')
+                    state = ('local', agg)
+            pending.append(result if result is not None else state[1])
+        groups = {}
+        for idx, o in enumerate(pending):
+            if isinstance(o, tuple):
+                groups.setdefault(id(o[1]), []).append(idx)
+        for members in groups.values():
+            rel = pending[members[0]][1]
+            ts = [pending[m][2] for m in members]
+            t_cat = ts[0] if len(ts) == 1 else torch.cat(ts, dim=1)
+            table = all_gather_rows(t_cat, self.group)                 # ONE all-gather per relation group
+            bias = torch.cat([pending[m][0].post_bias() for m in members])
+            agg = shard_aggregate(table, rel, 'rm', bias)
+            parts = torch.split(agg, [t.shape[1] for t in ts], dim=1) if len(ts) > 1 else (agg,)
+            for m, part in zip(members, parts):
+                layer, _, _, loc = pending[m]
+                pending[m] = layer.finish(part, loc, False)
+        return pending
+
+    def forward(self, metapath_idx=None):
+        model = self.model
+        z = torch.stack(self.channel_outputs(), dim=1)                 # [rows_per_rank, P, repr]
+        att = model.att if model.channel_aggr == 'att' else None
+        fused_local = F_.fuse_channels(z, att, model.channel_aggr, metapath_idx)
+        fused_rm = all_gather_rows(fused_local, self.group)            # [padded, repr], rank-major
+        return fused_rm.index_select(0, self.rm_of_global)             # node-id order, as the API promises
+
+
+def shard_model(model, world_size=None, rank=None, group=None):
+    """Switch a PEAGCN / PEASage model to row-sharded propagation.  ``model.forward`` keeps its
+    signature and still returns the full [N, repr] representation in node-id order."""
+    world_size = dist.get_world_size(group) if world_size is None else world_size
+    rank = dist.get_rank(group) if rank is None else rank
+    plan = ShardPlan(model.x.shape[0], world_size, rank)
+    model._sharded = ShardedPropagation(model, plan, group)
+    return model

@@ -69,13 +69,22 @@ class PEABaseChannel(torch.nn.Module):
     def forward(self, x, edge_index_list, shared=None):
         """relu(conv_s(x)) for every step but the last (reference models/base.py:134-140); the
         relu is fused into the conv's epilogue.  ``shared`` memoises first-step aggregations."""
+        out = self.forward_split(x, edge_index_list, shared, allow_split=False)
+        return out
+
+    def forward_split(self, x, edge_index_list, shared=None, allow_split=True):
+        """Runs the channel; if the last layer is of the project-then-aggregate kind and
+        ``allow_split``, stops after its projection and returns ``(layer, graph, projected, layer_input)``
+        so the model can aggregate all channels that share that relation in one launch."""
         assert len(edge_index_list) == self.num_steps
         n = x.size(0)
         for step_idx in range(self.num_steps):
             layer = self.gnn_layers[step_idx]
             ei = edge_index_list[step_idx]
-            relu = step_idx < self.num_steps - 1
+            last = step_idx == self.num_steps - 1
             g = get_graph(ei, n, keep_self_loops=getattr(layer, 'keeps_self_loops', False))
+            if last and allow_split and getattr(layer, 'splits', False):
+                return layer, g, layer.project(x), x
             kw = {}
             if step_idx == 0 and shared is not None and getattr(layer, 'shares_aggregate', None):
                 key = (layer.shares_aggregate, id(g))
@@ -83,7 +92,7 @@ class PEABaseChannel(torch.nn.Module):
                     if key not in shared:
                         shared[key] = layer.aggregate_input(x, g)
                     kw['aggregated'] = shared[key]
-            x = layer(x, ei, relu=relu, graph=g, **kw)
+            x = layer(x, ei, relu=not last, graph=g, **kw)
         return x
 
 
@@ -136,17 +145,38 @@ class PEABaseRecsysModel(GraphRecsysModel):
         if self.channel_aggr == 'att':
             glorot(self.att)
 
+    batch_last_step = True     # one aggregation per distinct last-step relation (columns concatenated)
+
     def channel_outputs(self):
         x = self.x
         shared = {}
-        return [module(x, self.meta_path_edge_index_list[idx], shared)
+        outs = [module.forward_split(x, self.meta_path_edge_index_list[idx], shared, self.batch_last_step)
                 for idx, module in enumerate(self.pea_channels)]
+        groups = {}
+        for idx, o in enumerate(outs):
+            if isinstance(o, tuple):
+                groups.setdefault(id(o[1]), []).append(idx)
+        for members in groups.values():
+            layer0, g = outs[members[0]][0], outs[members[0]][1]
+            if len(members) == 1:
+                t_cat = outs[members[0]][2]
+            else:
+                t_cat = torch.cat([outs[m][2] for m in members], dim=1)
+            agg = layer0.batched_aggregate(t_cat, g, [outs[m][0].post_bias() for m in members], False)
+            widths = [outs[m][2].shape[1] for m in members]
+            parts = torch.split(agg, widths, dim=1) if len(members) > 1 else (agg,)
+            for m, part in zip(members, parts):
+                layer, _, _, x_in = outs[m]
+                outs[m] = layer.finish(part, x_in, False)
+        return outs
 
     def forward(self, metapath_idx=None):
         """reference models/base.py:191-206.  'att' and 'mean' are the fusions that work upstream
         ('cat' / 'concat' disagree between _init and forward there and raise)."""
         if self.channel_aggr not in ('att', 'mean'):
             raise NotImplementedError('Other aggr methods not implemeted!')
+        if getattr(self, '_sharded', None) is not None:      # distributed.shard_model(): row-sharded propagation
+            return self._sharded.forward(metapath_idx)
         z = torch.stack(self.channel_outputs(), dim=1)                  # [N, P, repr]
         att = self.att if self.channel_aggr == 'att' else None
         return F_.fuse_channels(z, att, self.channel_aggr, metapath_idx)

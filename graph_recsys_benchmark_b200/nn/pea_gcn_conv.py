@@ -40,5 +40,23 @@ class PEAGCNConv(torch.nn.Module):
         h = F_.linear(x, self.weight, None, w_is_out_in=False)
         return F_.gcn_aggregate(h, g, self.bias, relu=relu)
 
+    # -- split form of the project-then-aggregate order (in > out), used by the model to run ONE
+    #    aggregation for all metapaths whose step shares a relation (columns concatenated) --------
+    @property
+    def splits(self):
+        return self.in_channels > self.out_channels
+
+    def project(self, x):
+        return F_.linear(x, self.weight, None, w_is_out_in=False)
+
+    def batched_aggregate(self, t_cat, g, biases, relu):
+        return F_.gcn_aggregate(t_cat, g, torch.cat(biases), relu=relu)
+
+    def post_bias(self):
+        return self.bias
+
+    def finish(self, agg, x, relu):
+        return agg
+
     def __repr__(self):
         return '{}({}, {})'.format(self.__class__.__name__, self.in_channels, self.out_channels)

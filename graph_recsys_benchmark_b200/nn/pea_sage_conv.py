@@ -33,5 +33,22 @@ class PEASageConv(torch.nn.Module):
             rel = F_.sage_mean_aggregate(t, g, self.lin_rel.bias)
         return F_.linear_accumulate(x, self.lin_root.weight, rel, relu=relu)
 
+    # -- split form (in > out): see PEAGCNConv ------------------------------------------------------
+    @property
+    def splits(self):
+        return self.in_channels > self.out_channels
+
+    def project(self, x):
+        return F_.linear(x, self.lin_rel.weight, None, w_is_out_in=True)
+
+    def batched_aggregate(self, t_cat, g, biases, relu):
+        return F_.sage_mean_aggregate(t_cat, g, torch.cat(biases))      # relu comes after the root term
+
+    def post_bias(self):
+        return self.lin_rel.bias
+
+    def finish(self, agg, x, relu):
+        return F_.linear_accumulate(x, self.lin_root.weight, agg.contiguous(), relu=relu)
+
     def __repr__(self):
         return '{}({}, {})'.format(self.__class__.__name__, self.in_channels, self.out_channels)

@@ -1,0 +1,92 @@
+"""GPU: the row-sharded propagation (distributed.shard_model) against the unsharded model.
+Two ranks share cuda:0 and talk over gloo (NCCL refuses two ranks on one device); the arithmetic
+and the collective pattern are exactly those of the NCCL run, only the transport differs."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, kind, entity_aware, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from helpers import product_model_for
+        from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+        from graph_recsys_benchmark_b200.distributed import shard_model, allreduce_gradients
+        torch.cuda.set_device(0)
+        ds = SyntheticHIN('tiny', seed=7, entity_aware=entity_aware)
+        torch.manual_seed(2020)
+        model = product_model_for(ds, kind, entity_aware=entity_aware)
+        import random, numpy as np
+        random.seed(1); np.random.seed(1); torch.manual_seed(1)
+        ds.cf_negative_sampling()
+        full = ds.get_batch(list(range(256))).cuda()
+        mine = full[rank::world].contiguous()                  # data-parallel split of the global batch
+        model.train()
+        ref_state = {k: v.clone() for k, v in model.state_dict().items()}
+        # unsharded reference on the whole global batch (same process, rank 0 only reports it)
+        loss_ref = model.loss(full)
+        loss_ref.backward()
+        ref_grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+        ref_repr = model.cached_repr.detach().clone()
+        model.zero_grad()
+        shard_model(model, world, rank)
+        loss = model.loss(mine)
+        loss.backward()
+        allreduce_gradients(list(model.parameters()))
+        total = loss.detach().clone()
+        dist.all_reduce(total)
+        torch.cuda.synchronize()
+
+        def rel(a, b):
+            return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
+        ret[rank] = dict(
+            loss=abs(total.item() - loss_ref.item()) / abs(loss_ref.item()),
+            repr=rel(model.cached_repr, ref_repr),
+            grads={n: rel(p.grad, ref_grads[n]) for n, p in model.named_parameters()
+                   if float(ref_grads[n].abs().max()) > 1e-10},
+        )
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('kind,entity_aware', [('gcn', False), ('sage', True)])
+@pytest.mark.parametrize('world', [2, 3])
+def test_sharded_model_matches_unsharded(kind, entity_aware, world):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), kind, entity_aware, ret), nprocs=world, join=True)
+    for r in range(world):
+        out = ret[r]
+        assert out['loss'] < 1e-5, out
+        assert out['repr'] < 1e-5, out
+        for name, e in out['grads'].items():
+            assert e < 1e-4, (name, e)
+
+
+def test_gat_sharding_is_refused_loudly():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import product_model_for
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+    from graph_recsys_benchmark_b200.distributed import shard_model
+    model = product_model_for(SyntheticHIN('tiny', seed=7), 'gat')
+    with pytest.raises(NotImplementedError):
+        shard_model(model, 2, 0)
