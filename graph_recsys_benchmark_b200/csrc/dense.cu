@@ -450,8 +450,9 @@ extern "C" int peagnn_linear_wgrad(const float* X, int64_t ldx, const float* dY,
                                    int w_is_out_in, float* dW, float* db, float* workspace,
                                    size_t workspace_floats, peagnn_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  PEAGNN_REQUIRE(K >= 0 && M > 0 && M <= 128 && K <= 128 && is_pow2(M) && (K == 0 || is_pow2(K)) && M >= 4 && (K == 0 || K >= 4),
-                 "peagnn_linear_wgrad: K=%d, M=%d must be powers of two in [4, 128] (K may be 0)", K, M);
+  PEAGNN_REQUIRE((K == 0 && M >= 4 && M % 4 == 0 && M <= 256) ||
+                     (K >= 4 && K <= 128 && is_pow2(K) && M >= 4 && M <= 128 && is_pow2(M)),
+                 "peagnn_linear_wgrad: K=%d, M=%d must be powers of two in [4, 128] (or K = 0 with M a multiple of 4, <= 256)", K, M);
   PEAGNN_REQUIRE(dY && workspace && ldd >= M && (K == 0 || (X && ldx >= K)), "peagnn_linear_wgrad: bad pointers");
   PEAGNN_REQUIRE(aligned16(dY) && ldd % 4 == 0 && (K == 0 || (aligned16(X) && ldx % 4 == 0)) && (!mask || (aligned16(mask) && ldm % 4 == 0)),
                  "peagnn_linear_wgrad: alignment");
