@@ -247,10 +247,19 @@ def run_product(args):
             torch.cuda.synchronize()
 
     # bring the SM clocks out of idle before anything is timed (the graph build above is host work)
+    # (learning rate 0 while spinning: the same kernels run, the weights stay at their initial values)
+    for gr in opt.param_groups:
+        gr['lr'] = 0.0
     t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < args.prewarm:
+    spin = torch.tensor([0.0], device=dev)
+    while spin.item() < 0.5:
         step(dev_batches[0])
         torch.cuda.synchronize()
+        spin[0] = 1.0 if time.perf_counter() - t_spin >= args.prewarm else 0.0
+        if world > 1:
+            dist.all_reduce(spin, op=dist.ReduceOp.MIN)       # every rank leaves the loop together
+    for gr in opt.param_groups:
+        gr['lr'] = 1e-3
     for k in range(W):
         step(dev_batches[k])
     barrier()
