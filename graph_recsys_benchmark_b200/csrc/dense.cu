@@ -6,6 +6,7 @@
 // kept full), and fp32 keeps the 1e-5 parity bar that TF32 tensor-core inputs would break.
 #include <algorithm>
 #include "common.cuh"
+#include "dense_v2.cuh"
 
 namespace peagnn {
 
@@ -245,25 +246,40 @@ __global__ void __launch_bounds__(kLinThreads) colsum_kernel(const float* __rest
                                                              const float* __restrict__ mask, int64_t ldm,
                                                              int64_t n_rows, int M, int64_t rows_per_cta,
                                                              float* __restrict__ partial /* [grid][M] */) {
-  __shared__ float red[kLinThreads];
-  const int lanes = kLinThreads / M * M;  // threads used; thread -> column t % M, row lane t / M
-  const int RL = kLinThreads / M;
+  // thread -> float4 column c4 = t % (M/4), row lane t / (M/4); four rows in flight per thread
+  __shared__ __align__(16) float red[kLinThreads * 4];
+  const int m4 = M / 4;
+  const int RL = kLinThreads / m4;
+  const int c4 = threadIdx.x % m4, rl = threadIdx.x / m4;
   const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t r_end = imin64(n_rows, r_begin + rows_per_cta);
-  float s = 0.f;
-  const int c = threadIdx.x % M, rl = threadIdx.x / M;
-  if ((int)threadIdx.x < lanes) {
-    for (int64_t r = r_begin + rl; r < r_end; r += RL) {
-      float v = __ldg(dY + r * ldd + c);
-      if (mask && !(__ldg(mask + r * ldm + c) > 0.f)) v = 0.f;
-      s += v;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rl < RL) {
+    for (int64_t r0 = r_begin + rl; r0 < r_end; r0 += 4 * RL) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t r = r0 + (int64_t)u * RL;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < r_end) {
+          v[u] = ldg4(dY + r * ldd + 4 * c4);
+          if (mask) {
+            const float4 g = ldg4(mask + r * ldm + 4 * c4);
+            v[u].x = g.x > 0.f ? v[u].x : 0.f; v[u].y = g.y > 0.f ? v[u].y : 0.f;
+            v[u].z = g.z > 0.f ? v[u].z : 0.f; v[u].w = g.w > 0.f ? v[u].w : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
     }
   }
-  red[threadIdx.x] = s;
+  st4(red + 4 * threadIdx.x, s);
   __syncthreads();
   if ((int)threadIdx.x < M) {
+    const int cc4 = threadIdx.x / 4, j = threadIdx.x % 4;
     float t = 0.f;
-    for (int q = 0; q < RL; ++q) t += red[q * M + threadIdx.x];
+    for (int q = 0; q < RL; ++q) t += red[4 * (q * m4 + cc4) + j];
     partial[(size_t)blockIdx.x * M + threadIdx.x] = t;
   }
 }
@@ -432,6 +448,20 @@ extern "C" int peagnn_linear(const float* X, int64_t ldx, const float* mask, int
                  "peagnn_linear: pointers must be 16-byte aligned");
   if (n == 0) return PEAGNN_OK;
   const int tx = pow2_ge(M / 4);
+  if ((K == 64 || K == 16) && tx <= 16) {   // hot shapes: prefetching register-tile kernels
+#define PEAGNN_LIN2(K_, TX_, RPT_) \
+  return launch_linear_v2<K_, TX_, RPT_>(X, ldx, mask, ldm, n, M, W, w_is_out_in, bias, relu, accumulate, Y, ldy, stream)
+    if (K == 64) {
+      if (tx <= 4) PEAGNN_LIN2(64, 4, 2);
+      if (tx == 8) PEAGNN_LIN2(64, 8, 4);
+      PEAGNN_LIN2(64, 16, 8);
+    } else {
+      if (tx <= 4) PEAGNN_LIN2(16, 4, 2);
+      if (tx == 8) PEAGNN_LIN2(16, 8, 4);
+      PEAGNN_LIN2(16, 16, 8);
+    }
+#undef PEAGNN_LIN2
+  }
 #define PEAGNN_LIN_CASE(TX_) \
   return launch_linear<TX_>(X, ldx, mask, ldm, n, K, M, W, w_is_out_in, bias, relu, accumulate, Y, ldy, stream)
   if (tx <= 4) PEAGNN_LIN_CASE(4);
@@ -467,6 +497,16 @@ extern "C" int peagnn_linear_wgrad(const float* X, int64_t ldx, const float* dY,
     if (dW && KM) cudaMemsetAsync(dW, 0, sizeof(float) * KM, stream);
     if (db) cudaMemsetAsync(db, 0, sizeof(float) * M, stream);
     return check_launch("peagnn_linear_wgrad(memset)");
+  }
+  if (K == 64 && (M == 64 || M == 32 || M == 16)) {   // hot shapes
+    const int64_t rpc = ((n + parts - 1) / parts + kWg2Rows - 1) / kWg2Rows * kWg2Rows;
+    int rc2;
+    if (M == 64) rc2 = launch_wgrad_v2<64, 64>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
+    else if (M == 32) rc2 = launch_wgrad_v2<64, 32>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
+    else rc2 = launch_wgrad_v2<64, 16>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
+    if (rc2) return rc2;
+    wgrad_finalize_v2_kernel<<<(KM + M + 63) / 64, 256, 0, stream>>>(workspace, parts, K, M, w_is_out_in, dW, db);
+    return check_launch("peagnn_linear_wgrad(v2 stage2)");
   }
   if (K == 0) {
     colsum_kernel<<<parts, kLinThreads, 0, stream>>>(dY, ldd, mask, ldm, n, M, rows_per_cta, workspace);

@@ -1,0 +1,134 @@
+"""GPU, BASELINE.json full sizes (MovieLens-25M-shaped HIN, N = 291,120, 23 M interactions): the
+oracle cannot run here in seconds, so parity is checked through size-independent properties -
+sortedness / stability of the CSR, adjointness of the forward and backward structures, linearity,
+closed forms for constant inputs, and an independent torch.sort ranking of every user."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(scope='module')
+def big():
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+    from graph_recsys_benchmark_b200.graph import RelationGraph
+    ds = SyntheticHIN('ml-25m', seed=1234)
+    ei = torch.from_numpy(ds.edge_index_nps['user2item']).long().to(DEV)
+    g = RelationGraph.from_edge_index(ei, ds.num_nodes)
+    return ds, ei, g
+
+
+def test_csr_sorted_stable_and_complete(big):
+    ds, ei, g = big
+    n, e = ds.num_nodes, ei.shape[1]
+    for csr, key in ((g.fwd, ei[1]), (g.bwd, ei[0])):
+        rp = csr.rowptr.long()
+        assert rp[0] == 0 and rp[-1] == e and bool((rp[1:] >= rp[:-1]).all())
+        eid = csr.eid.long()
+        k = key[eid]
+        assert bool((k[1:] >= k[:-1]).all())                                   # grouped by key
+        same = k[1:] == k[:-1]
+        assert bool((eid[1:][same] > eid[:-1][same]).all())                    # stable inside a row
+        assert torch.equal(torch.sort(eid).values, torch.arange(e, device=DEV))  # a permutation
+        assert torch.equal(torch.bincount(key, minlength=n), rp[1:] - rp[:-1])
+        other = ei[0] if key is ei[1] else ei[1]
+        assert torch.equal(csr.col.long(), other[eid])
+    assert g.fwd.n_heavy > 1000 and g.fwd.n_chunks > g.fwd.n_heavy            # the heavy path is exercised
+
+
+@pytest.mark.parametrize('feat', [16, 64, 112])
+def test_forward_and_backward_structures_are_adjoint(big, feat):
+    """<A x, y> == <x, A^T y> for the GCN-normalised operator: fwd CSR vs bwd CSR at full size."""
+    from graph_recsys_benchmark_b200 import functional as F_
+    ds, ei, g = big
+    n = ds.num_nodes
+    gen = torch.Generator(device=DEV).manual_seed(feat)
+    x = torch.randn(n, feat, device=DEV, generator=gen)
+    y = torch.randn(n, feat, device=DEV, generator=gen)
+    dis = g.gcn_dis
+    ax = F_.spmm_raw(g.fwd, x, feat, torch.empty_like(x), dis, dis, True)
+    aty = F_.spmm_raw(g.bwd, y, feat, torch.empty_like(y), dis, dis, True)
+    lhs = (ax.double() * y.double()).sum().item()
+    rhs = (x.double() * aty.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0)
+
+
+def test_aggregation_is_linear_and_matches_closed_form_on_constants(big):
+    from graph_recsys_benchmark_b200 import functional as F_
+    ds, ei, g = big
+    n, feat = ds.num_nodes, 16
+    dis = g.gcn_dis
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(n, feat, device=DEV, generator=gen)
+    y = torch.randn(n, feat, device=DEV, generator=gen)
+    agg = lambda t: F_.spmm_raw(g.fwd, t.contiguous(), feat, torch.empty(n, feat, device=DEV), dis, dis, True)
+    lin = agg(2.0 * x - 0.5 * y)
+    ref = 2.0 * agg(x) - 0.5 * agg(y)
+    assert float((lin - ref).abs().max() / ref.abs().max()) < 1e-5
+    # constant input: out[i] = dis[i] * (sum_{e -> i} dis[src_e] + dis[i]), by an independent torch reduction
+    ones = torch.ones(n, feat, device=DEV)
+    want = dis.double() * (torch.zeros(n, device=DEV, dtype=torch.float64).index_add_(0, ei[1], dis.double()[ei[0]]) + dis.double())
+    got = agg(ones)
+    assert float((got[:, 0].double() - want).abs().max() / want.abs().max()) < 1e-5
+    assert float((got - got[:, :1]).abs().max()) == 0.0                         # every column identical
+    # degrees: PyG-1.5.0 source-side degree + self loop
+    deg = torch.bincount(ei[0], minlength=n).double() + 1
+    assert float((dis.double() - deg.pow(-0.5)).abs().max()) < 1e-7
+    # SAGE mean of ones over rows with in-edges is exactly 1, rows without are exactly 0
+    mean = F_.spmm_raw(g.fwd, ones, feat, torch.empty(n, feat, device=DEV), g.inv_in_degree, None, False)
+    has = torch.bincount(ei[1], minlength=n) > 0
+    assert float((mean[has] - 1).abs().max()) < 1e-5 and float(mean[~has].abs().max()) == 0.0
+
+
+def test_eval_ranker_on_every_user_matches_torch_sort(big):
+    from graph_recsys_benchmark_b200 import functional as F_
+    ds, _, _ = big
+    n, D, C = ds.num_nodes, 16, 100
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    r = torch.randn(n, D, device=DEV, generator=gen)
+    fc1, fc2 = torch.nn.Linear(2 * D, D).to(DEV), torch.nn.Linear(D, 1).to(DEV)
+    U = ds.num_uids
+    users = torch.arange(U, device=DEV)
+    cand = torch.randint(ds.type_accs['iid'], ds.type_accs['iid'] + ds.num_iids, (U, C), device=DEV, generator=gen)
+    cand[:, 0] = torch.from_numpy(ds._test_items).to(DEV)
+    per_user, means, scores = F_.eval_rank(r, users, cand, 1, fc1.weight.detach(), fc1.bias.detach(),
+                                           fc2.weight.detach(), fc2.bias.detach(), return_scores=True)
+    order = torch.sort(scores, dim=1, descending=True, stable=True).indices
+    rank = (order == 0).float().argmax(dim=1)
+    assert torch.equal(per_user[:, 34].long(), rank)                            # bit-exact ranks, 162k users
+    for k in (5, 10, 20):
+        assert torch.equal(per_user[:, k - 5] > 0, rank < k)
+    ndcg10 = torch.where(rank < 10, 1.0 / torch.log2(rank.double() + 2), torch.zeros_like(rank, dtype=torch.float64))
+    assert float((per_user[:, 16 + 5] - ndcg10).abs().max()) < 1e-14
+    assert abs(means[5].item() - (rank < 10).double().mean().item()) < 1e-12
+    auc = (scores[:, :1] > scores[:, 1:]).double().mean(dim=1)
+    assert float((per_user[:, 32] - auc).abs().max()) < 1e-14
+
+
+def test_full_size_train_step_is_finite_and_reproducible(big):
+    """Two identical steps from identical state give bit-identical losses and gradients (the
+    aggregation is atomic-free; only the B-row BPR scatter uses float atomics)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import product_model_for
+    ds, _, _ = big
+    torch.manual_seed(5)
+    model = product_model_for(ds, 'gcn')
+    u2i = ds.edge_index_nps['user2item']
+    rng = np.random.RandomState(0)
+    sel = rng.randint(0, u2i.shape[1], 4096)
+    batch = torch.from_numpy(np.stack([u2i[0][sel], u2i[1][sel],
+                                       rng.randint(ds.type_accs['iid'], ds.type_accs['iid'] + ds.num_iids, 4096)], 1)).long().to(DEV)
+    model.train()
+    outs = []
+    for _ in range(2):
+        model.zero_grad()
+        loss = model.loss(batch)
+        loss.backward()
+        outs.append((loss.item(), model.cached_repr.clone(), model.pea_channels[0].gnn_layers[0].weight.grad.clone()))
+    assert np.isfinite(outs[0][0]) and outs[0][0] > 0
+    assert outs[0][0] == outs[1][0]
+    assert torch.equal(outs[0][1], outs[1][1])                                  # propagation is deterministic
+    assert float((outs[0][2] - outs[1][2]).abs().max() / outs[0][2].abs().max()) < 1e-5
