@@ -23,7 +23,7 @@ def big():
 def test_csr_sorted_stable_and_complete(big):
     ds, ei, g = big
     n, e = ds.num_nodes, ei.shape[1]
-    for csr, key in ((g.fwd, ei[1]), (g.bwd, ei[0])):
+    for csr, key, other in ((g.fwd, ei[1], ei[0]), (g.bwd, ei[0], ei[1])):
         rp = csr.rowptr.long()
         assert rp[0] == 0 and rp[-1] == e and bool((rp[1:] >= rp[:-1]).all())
         eid = csr.eid.long()
@@ -33,7 +33,6 @@ def test_csr_sorted_stable_and_complete(big):
         assert bool((eid[1:][same] > eid[:-1][same]).all())                    # stable inside a row
         assert torch.equal(torch.sort(eid).values, torch.arange(e, device=DEV))  # a permutation
         assert torch.equal(torch.bincount(key, minlength=n), rp[1:] - rp[:-1])
-        other = ei[0] if key is ei[1] else ei[1]
         assert torch.equal(csr.col.long(), other[eid])
     assert g.fwd.n_heavy > 1000 and g.fwd.n_chunks > g.fwd.n_heavy            # the heavy path is exercised
 
