@@ -175,7 +175,7 @@ def run_reference(args):
         'cpu_baseline': {'value': value, 'unit': 'triples/s', 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'triples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def full_over_lite_ratio(workload, ds_lite):
@@ -350,13 +350,29 @@ def run_product(args):
                 'value': B / (t_lite * ratio), 'unit': 'triples/s', 'cores': threads, 'kind': 'port',
                 'sample': '1 train step of the CPU oracle on the %s graph (%.1f s), scaled by the interaction ratio %.1f'
                           % (LITE.get(args.workload), t_lite, ratio)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    # Libraries (NCCL's version banner, tqdm, ...) may print to fd 1; keep stdout clean for the JSON line
+    # by pointing fd 1 at stderr for the rest of the run.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.impl == 'reference':
         run_reference(args)
     else:
