@@ -40,6 +40,7 @@ struct Edge {
 
 constexpr int kCtaThreads = 256;
 constexpr int kWarpsPerCta = kCtaThreads / 32;
+constexpr int kRowsPerWarp = 8;     // consecutive light rows handled by one warp of csr_rows_kernel
 constexpr unsigned kFull = 0xffffffffu;
 
 template <class Op>
@@ -153,8 +154,8 @@ __global__ void __launch_bounds__(kCtaThreads) csr_chunk_kernel(const peagnn_csr
   }
 }
 
-// Launch 2: the first blocks fold the heavy rows' chunk partials, the rest take one light row
-// per warp.
+// Launch 2: the first blocks fold the heavy rows' chunk partials, the rest take kRowsPerWarp light
+// rows per warp.
 template <class Op, int G>
 __global__ void __launch_bounds__(kCtaThreads) csr_rows_kernel(const peagnn_csr_t g, const Op op_in) {
   Op op = op_in;
@@ -185,16 +186,57 @@ __global__ void __launch_bounds__(kCtaThreads) csr_rows_kernel(const peagnn_csr_
     op.finish(acc, i, h, gl, writer);
     return;
   }
-  const long long lr = ((long long)blockIdx.x - heavy_blocks) * kWarpsPerCta + warp;
-  if (lr >= (long long)g.nrows * heads) return;
-  const int i = (int)(lr / heads);
-  const int h = (int)(lr - (long long)i * heads);
-  const int start = g.rowptr[i], end = g.rowptr[i + 1];
-  if (g.n_heavy > 0 && end - start > g.heavy_threshold) return;  // folded above
-  op.row_begin(i, h, gl);
-  process_batches<Op, G>(op, g.col, start, end, 32, acc, lane, g.row_offset + i);
-  fold_slots<Op, G>(acc);
-  op.finish(acc, i, h, gl, writer);
+  // Light rows: each warp takes kRowsPerWarp consecutive logical rows.  Rows WITHOUT edges (most
+  // rows of most relations: every node that is not a target of the relation) only need the
+  // epilogue; they are handed to the warp's slots 32/G at a time so that several rows' loads and
+  // stores are in flight together.  Rows with edges then run one at a time on the whole warp.
+  constexpr int EPW = 32 / G;
+  const long long total = (long long)g.nrows * heads;
+  const long long lr0 = (((long long)blockIdx.x - heavy_blocks) * kWarpsPerCta + warp) * kRowsPerWarp;
+  if (lr0 >= total) return;
+  const long long my_lr = lr0 + lane;
+  const bool mine = lane < kRowsPerWarp && my_lr < total;
+  int start_l = 0, end_l = 0;
+  if (mine) {
+    const int i_l = (int)(my_lr / heads);
+    start_l = g.rowptr[i_l];
+    end_l = g.rowptr[i_l + 1];
+  }
+  const int deg_l = end_l - start_l;
+  const bool heavy_l = g.n_heavy > 0 && deg_l > g.heavy_threshold;   // folded above
+  const unsigned empty_mask = __ballot_sync(kFull, mine && deg_l == 0);
+  unsigned work_mask = __ballot_sync(kFull, mine && deg_l > 0 && !heavy_l);
+
+  const int n_empty = __popc(empty_mask);
+  const int slot = lane / G;
+  for (int base = 0; base < n_empty; base += EPW) {
+    const int k = base + slot;
+    const bool has = k < n_empty;
+    const int src_lane = has ? (int)__fns(empty_mask, 0, k + 1) : (int)__fns(empty_mask, 0, 1);
+    const long long lr = lr0 + src_lane;
+    const int i = (int)(lr / heads);
+    const int h = (int)(lr - (long long)i * heads);
+    float e_acc[Op::NV];
+#pragma unroll
+    for (int v = 0; v < Op::NV; ++v) e_acc[v] = identity<Op>();
+    op.row_begin(i, h, gl);            // slots hold different rows here; shuffles stay inside a slot
+    op.finish(e_acc, i, h, gl, has);
+  }
+  while (work_mask) {
+    const int l = __ffs(work_mask) - 1;
+    work_mask &= work_mask - 1;
+    const long long lr = lr0 + l;
+    const int i = (int)(lr / heads);
+    const int h = (int)(lr - (long long)i * heads);
+    const int start = __shfl_sync(kFull, start_l, l);
+    const int end = __shfl_sync(kFull, end_l, l);
+#pragma unroll
+    for (int v = 0; v < Op::NV; ++v) acc[v] = identity<Op>();
+    op.row_begin(i, h, gl);
+    process_batches<Op, G>(op, g.col, start, end, 32, acc, lane, g.row_offset + i);
+    fold_slots<Op, G>(acc);
+    op.finish(acc, i, h, gl, writer);
+  }
 }
 
 template <class Op, int G>
@@ -209,7 +251,8 @@ int launch_csr(const peagnn_csr_t& g, const Op& op, cudaStream_t stream, const c
     if (rc) return rc;
   }
   const long long heavy_blocks = ((long long)g.n_heavy * heads + kWarpsPerCta - 1) / kWarpsPerCta;
-  const long long light_blocks = ((long long)g.nrows * heads + kWarpsPerCta - 1) / kWarpsPerCta;
+  const long long rows_per_block = (long long)kWarpsPerCta * kRowsPerWarp;
+  const long long light_blocks = ((long long)g.nrows * heads + rows_per_block - 1) / rows_per_block;
   const long long blocks = heavy_blocks + light_blocks;
   if (blocks == 0) return PEAGNN_OK;
   csr_rows_kernel<Op, G><<<(unsigned)blocks, kCtaThreads, 0, stream>>>(g, op);

@@ -115,3 +115,37 @@ def test_training_steps_and_metrics_follow_the_oracle(kind, entity_aware):
         assert np.array_equal(hr_m, hr_o) and np.allclose(nd_m, nd_o, rtol=1e-12)
     assert abs(hr_m[5] - hr_o[5]) <= 2.0 / len(per['ranks']) and abs(nd_m[5] - nd_o[5]) <= 2.0 / len(per['ranks'])
     assert abs(auc_m[0] - auc_o[0]) < 1e-3 and abs(l_m[0] - l_o[0]) / abs(l_o[0]) < 1e-4
+
+
+def test_experiment_cli_trains_evaluates_checkpoints_and_resumes(tmp_path, monkeypatch, capsys):
+    """reference experiments/peagcn_solver_bpr.py flags -> BaseSolver.run(): init eval, 2 epochs,
+    checkpoint + global logger written in the reference's layout, resume from latest.pkl."""
+    import glob
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'experiments'))
+    import pea_cli
+    from graph_recsys_benchmark_b200 import models
+    monkeypatch.chdir(tmp_path)
+    argv = ['--dataset=Movielens', '--dataset_name=latest-small', '--synthetic=tiny', '--sampling_strategy=unseen',
+            '--runs=1', '--epochs=2', '--batch_size=512', '--save_every_epoch=0', '--save_epochs=1',
+            '--metapath_test=false', '--num_workers=0']
+    pea_cli.run('PEAGCN', models.PEAGCNRecsysModel, argv=argv)
+    out = capsys.readouterr().out
+    assert 'Initial performance HR@5' in out and 'Run: 1, epoch: 2, HR@5' in out and 'Duration' in out
+    ck = glob.glob(os.path.join(str(tmp_path), 'checkpoint', 'weights', 'Movielenslatest-small', 'PEAGCN', 'BPR', '*', 'run_1', 'latest.pkl'))
+    assert len(ck) == 1
+    state = torch.load(ck[0], map_location='cpu', weights_only=False)
+    assert state['epoch'] == 2 and set(state) == {'epoch', 'model_states', 'optim_states', 'rec_metrics'}
+    assert state['rec_metrics'][0].shape == (2, 16) and 'pea_channels.0.gnn_layers.0.weight' in state['model_states']['model']
+    assert os.path.exists(os.path.join(os.path.dirname(ck[0]), '1.pkl'))
+    logs = glob.glob(os.path.join(str(tmp_path), 'checkpoint', 'loggers', '*', 'PEAGCN', 'BPR', '*', 'logger_file.txt'))
+    assert len(logs) == 1 and 'Run: 1, epoch: 1' in open(logs[0]).read()
+    # a finished run is not repeated (global_logger.pkl holds it)
+    pea_cli.run('PEAGCN', models.PEAGCNRecsysModel, argv=argv)
+    assert 'epoch: 1' not in capsys.readouterr().out
+    # a fresh logger folder with the old weights resumes at epoch 3
+    os.remove(os.path.join(os.path.dirname(logs[0]), 'global_logger.pkl'))
+    pea_cli.run('PEAGCN', models.PEAGCNRecsysModel, argv=[a if not a.startswith('--epochs') else '--epochs=3' for a in argv])
+    out = capsys.readouterr().out
+    assert "Loaded checkpoint_backup" in out and 'Run: 1, epoch: 3, HR@5' in out and 'Run: 1, epoch: 2, HR@5' not in out
