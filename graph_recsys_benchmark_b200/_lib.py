@@ -22,6 +22,7 @@ class CsrView(C.Structure):
         ('n_chunks', C.c_int32),
         ('chunk_row', C.c_void_p), ('chunk_begin', C.c_void_p), ('chunk_end', C.c_void_p),
         ('partial', C.c_void_p),
+        ('nnz', C.c_int64),
     ]
 
 

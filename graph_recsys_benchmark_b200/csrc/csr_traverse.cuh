@@ -40,7 +40,7 @@ struct Edge {
 
 constexpr int kCtaThreads = 256;
 constexpr int kWarpsPerCta = kCtaThreads / 32;
-constexpr int kRowsPerWarp = 8;     // consecutive light rows handled by one warp of csr_rows_kernel
+constexpr int kSparseRowsPerWarp = 8;  // light rows per warp when the view is sparse (avg degree < 8), else 1
 constexpr unsigned kFull = 0xffffffffu;
 
 template <class Op>
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kCtaThreads) csr_chunk_kernel(const peagnn_csr
 
 // Launch 2: the first blocks fold the heavy rows' chunk partials, the rest take kRowsPerWarp light
 // rows per warp.
-template <class Op, int G>
+template <class Op, int G, int RPW>
 __global__ void __launch_bounds__(kCtaThreads) csr_rows_kernel(const peagnn_csr_t g, const Op op_in) {
   Op op = op_in;
   const int heads = op.heads;
@@ -192,10 +192,10 @@ __global__ void __launch_bounds__(kCtaThreads) csr_rows_kernel(const peagnn_csr_
   // stores are in flight together.  Rows with edges then run one at a time on the whole warp.
   constexpr int EPW = 32 / G;
   const long long total = (long long)g.nrows * heads;
-  const long long lr0 = (((long long)blockIdx.x - heavy_blocks) * kWarpsPerCta + warp) * kRowsPerWarp;
+  const long long lr0 = (((long long)blockIdx.x - heavy_blocks) * kWarpsPerCta + warp) * RPW;
   if (lr0 >= total) return;
   const long long my_lr = lr0 + lane;
-  const bool mine = lane < kRowsPerWarp && my_lr < total;
+  const bool mine = lane < RPW && my_lr < total;
   int start_l = 0, end_l = 0;
   if (mine) {
     const int i_l = (int)(my_lr / heads);
@@ -251,11 +251,17 @@ int launch_csr(const peagnn_csr_t& g, const Op& op, cudaStream_t stream, const c
     if (rc) return rc;
   }
   const long long heavy_blocks = ((long long)g.n_heavy * heads + kWarpsPerCta - 1) / kWarpsPerCta;
-  const long long rows_per_block = (long long)kWarpsPerCta * kRowsPerWarp;
+  // sparse views (most rows have no edge) pack several rows per warp so that the edge-less rows'
+  // epilogues overlap; dense views keep one row per warp for parallelism and balance
+  const bool sparse = g.nnz > 0 && g.nnz < 8ll * g.nrows;
+  const long long rows_per_block = (long long)kWarpsPerCta * (sparse ? kSparseRowsPerWarp : 1);
   const long long light_blocks = ((long long)g.nrows * heads + rows_per_block - 1) / rows_per_block;
   const long long blocks = heavy_blocks + light_blocks;
   if (blocks == 0) return PEAGNN_OK;
-  csr_rows_kernel<Op, G><<<(unsigned)blocks, kCtaThreads, 0, stream>>>(g, op);
+  if (sparse)
+    csr_rows_kernel<Op, G, kSparseRowsPerWarp><<<(unsigned)blocks, kCtaThreads, 0, stream>>>(g, op);
+  else
+    csr_rows_kernel<Op, G, 1><<<(unsigned)blocks, kCtaThreads, 0, stream>>>(g, op);
   return check_launch(what);
 }
 

@@ -85,6 +85,7 @@ class Csr(object):
         v.rowptr = self.rowptr.data_ptr()
         v.col = self.col.data_ptr() if self.nnz else 0
         v.nrows = self.num_nodes
+        v.nnz = self.nnz
         v.row_offset = 0
         v.heavy_threshold = self.heavy_threshold
         v.n_heavy = self.n_heavy

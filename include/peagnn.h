@@ -83,6 +83,8 @@ typedef struct {
   const int32_t* chunk_begin;     /* [n_chunks] edge range of the chunk (absolute offsets)    */
   const int32_t* chunk_end;
   float* partial;                 /* workspace, >= peagnn_partial_floats(...) floats          */
+  int64_t nnz;                    /* edges of this view (scheduling hint: sparse views pack
+                                     several rows per warp); 0 = unknown                      */
 } peagnn_csr_t;
 
 /* Floats of `partial` workspace an aggregation of width F (per head) needs on this view. */
