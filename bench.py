@@ -306,6 +306,15 @@ def run_product(args):
             peaks = json.load(open(pk))
         hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
         peak_src = 'measured' if 'hbm_gbs' in peaks else 'fallback'
+        if os.environ.get('PEAGNN_BENCH_DUMP_SPMM'):
+            per = {}
+            for name, nb, a, b in prof_spmm:
+                d = per.setdefault(name, [0, 0.0, nb])
+                d[0] += 1
+                d[1] += a.elapsed_time(b)
+            for name, (cnt, ms, nb) in sorted(per.items(), key=lambda kv: -kv[1][1]):
+                sys.stderr.write('SPMM %-40s x%5.1f/step %8.3f ms/launch %8.1f GB/s\n'
+                                 % (name, cnt / K, ms / cnt, nb / (ms / cnt) / 1e6))
         agg_bytes = sum(p[1] for p in prof_spmm)
         agg_ms = sum(p[2].elapsed_time(p[3]) for p in prof_spmm)
         by_name = {}

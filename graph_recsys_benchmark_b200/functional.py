@@ -72,7 +72,7 @@ def spmm_raw(csr, X, feat, out, rs=None, cs=None, self_loop=False, bias=None, re
     else:
         nrows = view.nrows
         nnz = csr.nnz if hasattr(csr, 'nnz') else int(csr.rowptr[-1].item() - csr.rowptr[0].item())
-        _timed('spmm_f%d' % feat, spmm_algorithmic_bytes(nnz, nrows, feat, rs is not None, cs is not None,
+        _timed('spmm_f%d_e%d_n%d_h%d' % (feat, nnz, nrows, view.n_heavy), spmm_algorithmic_bytes(nnz, nrows, feat, rs is not None, cs is not None,
                                                          self_loop, accumulate), launch)
     return out
 

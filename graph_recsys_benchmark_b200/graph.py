@@ -18,8 +18,11 @@ import torch
 
 from . import _lib
 
-HEAVY_THRESHOLD = 1024     # rows with more edges than this are cut into chunks ...
+HEAVY_THRESHOLD = 256      # rows with more edges than this are cut into chunks (a single warp walking a longer
+                           # row becomes the critical path of the launch) ...
 CHUNK_EDGES = 4096         # ... of at most this many edges, one CTA each
+MIN_CHUNK_EDGES = 256
+SPARSE_HEAVY_THRESHOLD = 96
 
 
 def _ptr(t):
@@ -37,7 +40,9 @@ class Csr(object):
         self.rowptr, self.col, self.eid = rowptr, col, eid
         self.num_nodes = num_nodes
         self.nnz = int(col.numel())
-        self.heavy_threshold = HEAVY_THRESHOLD if heavy_threshold is None else heavy_threshold
+        if heavy_threshold is None:      # sparse views pack 8 rows per warp: keep those rows short
+            heavy_threshold = min(HEAVY_THRESHOLD, SPARSE_HEAVY_THRESHOLD) if self.nnz < 8 * num_nodes else HEAVY_THRESHOLD
+        self.heavy_threshold = heavy_threshold
         self.chunk_edges = CHUNK_EDGES if chunk_edges is None else chunk_edges
         self._build_work_list()
         self._partial = None
@@ -55,6 +60,11 @@ class Csr(object):
             self.n_chunks = 0
             return
         hdeg = deg[heavy]
+        # few very long rows (a genre / year / tag node as a target): shrink the chunks until there
+        # are about two CTAs per SM, so the row does not sit on a handful of SMs
+        heavy_edges = int(hdeg.sum().item())
+        fill = max(MIN_CHUNK_EDGES, (heavy_edges // (2 * 148) + 31) // 32 * 32)
+        self.chunk_edges = min(self.chunk_edges, fill)
         nch = (hdeg + self.chunk_edges - 1) // self.chunk_edges
         cptr = torch.zeros(self.n_heavy + 1, dtype=torch.long, device=dev)
         cptr[1:] = torch.cumsum(nch, 0)
