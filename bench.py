@@ -222,7 +222,7 @@ def run_product(args):
     dev_batches = host_batches.to(dev)
 
     sharded = False
-    if world > 1 and args.model in ('gcn', 'sage'):
+    if world > 1 and args.model in ('gcn', 'sage', 'gat'):
         from graph_recsys_benchmark_b200.distributed import shard_model
         shard_model(model, world, rank)
         sharded = True

@@ -22,6 +22,7 @@ struct RowMaxOp {
   float* __restrict__ rowmax;
   float slope;
   int row_offset;
+  int self_loop;   // add the implicit self loop (0 when the view stores self loops as edges)
   int h_;
 
   __device__ __forceinline__ void row_begin(int, int h, int) { h_ = h; }
@@ -37,7 +38,7 @@ struct RowMaxOp {
   }
   __device__ __forceinline__ void finish(float* acc, int i, int h, int, bool writer) const {
     const int64_t gi = (int64_t)(row_offset + i) * heads + h;
-    const float m = fmaxf(acc[0], __ldg(a_j + gi));  // the self loop
+    const float m = self_loop ? fmaxf(acc[0], __ldg(a_j + gi)) : acc[0];  // the self loop
     if (writer) rowmax[gi] = leaky(__ldg(a_i + gi) + m, slope);
   }
 };
@@ -61,6 +62,7 @@ struct GatAggOp {
   const float* __restrict__ bias;
   float slope;
   int row_offset, relu;
+  int self_loop;
   // per-row registers
   float ai_, m_;
   int h_;
@@ -96,7 +98,7 @@ struct GatAggOp {
   __device__ __forceinline__ void finish(float* acc, int i, int h, int gl, bool writer) const {
     if (!writer) return;
     const int64_t gi = (int64_t)(row_offset + i) * heads + h;
-    const float ws = expf(leaky(ai_ + __ldg(a_j + gi), slope) - m_);  // self loop, appended last
+    const float ws = self_loop ? expf(leaky(ai_ + __ldg(a_j + gi), slope) - m_) : 0.f;  // self loop, appended last
     const float den = acc[4 * CPL] + ws + 1e-16f;
     if (gl == 0 && denom) denom[gi] = den;
     const float inv = 1.f / den;
@@ -106,7 +108,7 @@ struct GatAggOp {
     for (int ch = 0; ch < CPL; ++ch) {
       const int idx = gl + ch * G;
       if (idx < f4) {
-        const float4 v = ldg4(xi + 4 * idx);
+        const float4 v = self_loop ? ldg4(xi + 4 * idx) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 a;
         a.x = fmaf(ws, v.x, acc[4 * ch + 0]) * inv;
         a.y = fmaf(ws, v.y, acc[4 * ch + 1]) * inv;
@@ -151,6 +153,7 @@ struct GatBwdDstOp {
   float* __restrict__ d_ai;
   float slope;
   int row_offset;
+  int self_loop;
   // per-row registers
   float ai_, m_, inv_den_, D_;
   int h_;
@@ -219,6 +222,10 @@ struct GatBwdDstOp {
   __device__ __forceinline__ void finish(float* acc, int i, int h, int gl, bool writer) const {
     const int64_t node = row_offset + i;
     const int64_t gi = node * heads + h;
+    if (!self_loop) {
+      if (writer && gl == 0) d_ai[gi] = acc[0];
+      return;
+    }
     float alpha;
     const float ds = edge_terms(node, ai_ + __ldg(a_j + gi), gl, alpha);
     if (writer && gl == 0) {
@@ -248,6 +255,7 @@ struct GatBwdSrcOp {
   int64_t ldh;
   float* __restrict__ d_aj;
   int row_offset;
+  int self_loop;
   int h_;
 
   __device__ __forceinline__ void row_begin(int, int h, int) { h_ = h; }
@@ -278,15 +286,15 @@ struct GatBwdSrcOp {
     if (!writer) return;
     const int64_t node = row_offset + i;
     const int64_t gi = node * heads + h;
-    const float ws = __ldg(alpha_self + gi);
-    if (gl == 0) d_aj[gi] = acc[4 * CPL] + __ldg(ds_self + gi);
+    const float ws = self_loop ? __ldg(alpha_self + gi) : 0.f;
+    if (gl == 0) d_aj[gi] = acc[4 * CPL] + (self_loop ? __ldg(ds_self + gi) : 0.f);
     const float* xi = dout + node * ldd + (int64_t)h * feat;
     float* o = dH + (int64_t)i * ldh + (int64_t)h * feat;
 #pragma unroll
     for (int ch = 0; ch < CPL; ++ch) {
       const int idx = gl + ch * G;
       if (idx < f4) {
-        const float4 v = ldg4(xi + 4 * idx);
+        const float4 v = self_loop ? ldg4(xi + 4 * idx) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 a;
         a.x = fmaf(ws, v.x, acc[4 * ch + 0]);
         a.y = fmaf(ws, v.y, acc[4 * ch + 1]);
@@ -327,7 +335,7 @@ extern "C" int peagnn_gat_rowmax(const peagnn_csr_t* g, const float* a_i, const 
   if (g->nrows == 0) return PEAGNN_OK;
   RowMaxOp op;
   op.heads = heads; op.a_i = a_i; op.a_j = a_j; op.rowmax = rowmax; op.slope = slope;
-  op.row_offset = g->row_offset; op.h_ = 0;
+  op.row_offset = g->row_offset; op.h_ = 0; op.self_loop = !g->explicit_self_loops;
   return launch_csr<RowMaxOp, 1>(*g, op, stream, "peagnn_gat_rowmax");
 }
 
@@ -347,7 +355,7 @@ extern "C" int peagnn_gat_aggregate(const peagnn_csr_t* g, const float* H, int64
     op.heads = heads; op.H = H; op.ldh = ldh; op.feat = feat; op.f4 = feat / 4; op.a_i = a_i;    \
     op.a_j = a_j; op.rowmax = rowmax; op.denom = denom; op.out = out; op.ldo = ldo;              \
     op.bias = bias; op.slope = slope; op.row_offset = g->row_offset; op.relu = relu;             \
-    op.ai_ = 0.f; op.m_ = 0.f; op.h_ = 0;                                                        \
+    op.ai_ = 0.f; op.m_ = 0.f; op.h_ = 0; op.self_loop = !g->explicit_self_loops;                \
     return launch_csr<GatAggOp<CPL_, G_>, G_>(*g, op, stream, "peagnn_gat_aggregate");           \
   }
   PEAGNN_GEOM_DISPATCH(feat, CALL);
@@ -364,7 +372,7 @@ extern "C" int peagnn_gat_backward_dst(const peagnn_csr_t* g, const float* H, in
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_gat_common(g, feat, heads, "peagnn_gat_backward_dst");
   if (rc) return rc;
-  PEAGNN_REQUIRE(H && a_i && a_j && rowmax && denom && agg && dout && alpha_self && ds_self && d_ai,
+  PEAGNN_REQUIRE(H && a_i && a_j && rowmax && denom && agg && dout && d_ai && (g->explicit_self_loops || (alpha_self && ds_self)),
                  "peagnn_gat_backward_dst: null pointer");
   PEAGNN_REQUIRE(ldh % 4 == 0 && lda % 4 == 0 && ldd % 4 == 0 && aligned16(H) && aligned16(agg) && aligned16(dout),
                  "peagnn_gat_backward_dst: alignment");
@@ -377,6 +385,7 @@ extern "C" int peagnn_gat_backward_dst(const peagnn_csr_t* g, const float* H, in
     op.agg_bias = agg_bias; op.dout = dout; op.ldd = ldd; op.alpha_e = alpha_e; op.ds_e = ds_e;    \
     op.alpha_self = alpha_self; op.ds_self = ds_self; op.d_ai = d_ai; op.slope = slope;            \
     op.row_offset = g->row_offset; op.ai_ = op.m_ = op.inv_den_ = op.D_ = 0.f; op.h_ = 0;          \
+    op.self_loop = !g->explicit_self_loops;                                                        \
     for (int q = 0; q < CPL_; ++q) op.g_[q] = make_float4(0.f, 0.f, 0.f, 0.f);                     \
     return launch_csr<GatBwdDstOp<CPL_, G_>, G_>(*g, op, stream, "peagnn_gat_backward_dst");       \
   }
@@ -392,7 +401,7 @@ extern "C" int peagnn_gat_backward_src(const peagnn_csr_t* gt, const int32_t* pe
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_gat_common(gt, feat, heads, "peagnn_gat_backward_src");
   if (rc) return rc;
-  PEAGNN_REQUIRE(alpha_self && ds_self && dout && dH && d_aj, "peagnn_gat_backward_src: null pointer");
+  PEAGNN_REQUIRE(dout && dH && d_aj && (gt->explicit_self_loops || (alpha_self && ds_self)), "peagnn_gat_backward_src: null pointer");
   PEAGNN_REQUIRE(ldh % 4 == 0 && ldd % 4 == 0 && aligned16(dH) && aligned16(dout), "peagnn_gat_backward_src: alignment");
   if (gt->nrows == 0) return PEAGNN_OK;
 #define CALL(CPL_, G_)                                                                              \
@@ -401,7 +410,7 @@ extern "C" int peagnn_gat_backward_src(const peagnn_csr_t* gt, const int32_t* pe
     op.heads = heads; op.perm = perm; op.alpha_e = alpha_e; op.ds_e = ds_e;                         \
     op.alpha_self = alpha_self; op.ds_self = ds_self; op.dout = dout; op.ldd = ldd;                 \
     op.feat = feat; op.f4 = feat / 4; op.dH = dH; op.ldh = ldh; op.d_aj = d_aj;                     \
-    op.row_offset = gt->row_offset; op.h_ = 0;                                                      \
+    op.row_offset = gt->row_offset; op.h_ = 0; op.self_loop = !gt->explicit_self_loops;             \
     return launch_csr<GatBwdSrcOp<CPL_, G_>, G_>(*gt, op, stream, "peagnn_gat_backward_src");       \
   }
   PEAGNN_GEOM_DISPATCH(feat, CALL);

@@ -92,7 +92,7 @@ static int run_spmm(const peagnn_csr_t& g, const float* X, int64_t ldx, int feat
   op.heads = 1;
   op.X = X; op.ldx = ldx; op.f4 = feat / 4; op.out = out; op.ldo = ldo;
   op.rs = rs; op.cs = cs; op.bias = bias; op.row_offset = g.row_offset;
-  op.self_loop = self_loop; op.relu = relu; op.accumulate = accumulate;
+  op.self_loop = self_loop && !g.explicit_self_loops; op.relu = relu; op.accumulate = accumulate;
   return launch_csr<SpmmOp<CPL, G>, G>(g, op, stream, "peagnn_spmm");
 }
 

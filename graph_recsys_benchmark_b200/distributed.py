@@ -83,36 +83,52 @@ class ShardedRelation(object):
         dev = edge_index.device
         n = plan.num_nodes
         src, dst = edge_index[0], edge_index[1]
-        nl = src != dst if kind == 'gcn' else torch.ones_like(src, dtype=torch.bool)
+        loops = kind in ('gcn', 'gat')      # these convs drop self-loop edges and add one loop per node
+        nl = src != dst if loops else torch.ones_like(src, dtype=torch.bool)
         if kind == 'gcn':
             deg = torch.bincount(src[nl], minlength=n).float() + 1.0       # source side + self loop
             scale = deg.pow(-0.5)
-        else:
+        elif kind == 'sage':
             cnt = torch.bincount(dst, minlength=n).float()
             scale = 1.0 / cnt.clamp(min=1.0)
+        else:
+            scale = torch.ones(n, device=dev)
         own = plan.local_global_ids(device=dev)
         valid = own >= 0
         self.scale_orig = scale.contiguous()
         rm_ids = plan.rank_major_to_global(dev)
         self.scale_rm = torch.where(rm_ids >= 0, scale[rm_ids.clamp(min=0)], torch.zeros_like(rm_ids, dtype=scale.dtype)).contiguous()
         self.scale_local = torch.where(valid, scale[own.clamp(min=0)], torch.zeros_like(own, dtype=scale.dtype)).contiguous()
-        self.src, self.dst_local = shard_coo(edge_index, plan, explicit_self_loops=(kind == 'gcn'),
-                                             drop_self_loops=(kind == 'gcn'))
-        self._fwd, self._bwd = {}, {}
+        self.src, self.dst_local = shard_coo(edge_index, plan, explicit_self_loops=loops, drop_self_loops=loops)
+        self.explicit_self_loops = loops
+        self._fwd, self._bwd, self._perm = {}, {}, {}
 
     def _cols(self, layout):
         return self.src if layout == 'orig' else self.plan.to_rank_major(self.src)
 
     def fwd(self, layout):
         if layout not in self._fwd:
-            self._fwd[layout] = build_csr(self.dst_local, self._cols(layout), self.plan.rows_per_rank, False)
+            csr = build_csr(self.dst_local, self._cols(layout), self.plan.rows_per_rank, False)
+            csr.explicit_self_loops = self.explicit_self_loops
+            self._fwd[layout] = csr
         return self._fwd[layout]
 
     def bwd(self, layout):
         if layout not in self._bwd:
             rows = self.plan.num_nodes if layout == 'orig' else self.plan.padded
-            self._bwd[layout] = build_csr(self._cols(layout), self.dst_local, rows, False)
+            csr = build_csr(self._cols(layout), self.dst_local, rows, False)
+            csr.explicit_self_loops = self.explicit_self_loops
+            self._bwd[layout] = csr
         return self._bwd[layout]
+
+    def bwd_to_fwd(self, layout):
+        """perm[k] = position in the target-grouped shard arrays of the k-th source-grouped edge."""
+        if layout not in self._perm:
+            f, b = self.fwd(layout), self.bwd(layout)
+            inv = torch.empty(max(int(self.src.numel()), 1), dtype=torch.int32, device=f.eid.device)
+            inv[f.eid.long()] = torch.arange(f.nnz, dtype=torch.int32, device=inv.device)
+            self._perm[layout] = inv[b.eid.long()].contiguous()
+        return self._perm[layout]
 
     def table_scale(self, layout):
         return self.scale_orig if layout == 'orig' else self.scale_rm
@@ -157,6 +173,69 @@ class _ShardAggregate(torch.autograd.Function):
 
 def shard_aggregate(X, rel, layout, bias=None):
     return _ShardAggregate.apply(X, bias, rel, layout)
+
+
+class _ShardGatAggregate(torch.autograd.Function):
+    """Owned rows of the GAT edge-softmax aggregate.  H [padded, heads*F] and a_j [padded, heads] are
+    rank-major tables, a_i [rows_per_rank, heads] is local; the shard stores self loops as edges."""
+
+    @staticmethod
+    def forward(ctx, H, ai, aj, bias, rel, heads, relu):
+        import ctypes as C
+        from . import _lib
+        from .graph import _ptr, _stream
+        H = F_._rows(F_._req(H, 'h'))
+        rpr = rel.plan.rows_per_rank
+        feat = H.shape[1] // heads
+        dev = H.device
+        ai, aj = ai.contiguous(), aj.contiguous()
+        rowmax = torch.empty(rpr, heads, dtype=torch.float32, device=dev)
+        denom = torch.empty_like(rowmax)
+        out = torch.empty(rpr, heads * feat, dtype=torch.float32, device=dev)
+        view = rel.fwd('rm').view(feat, heads)
+        with torch.cuda.device(dev):
+            _lib.call('peagnn_gat_rowmax', C.byref(view), _ptr(ai), _ptr(aj), heads, F_.NEG_SLOPE, _ptr(rowmax), _stream())
+            _lib.call('peagnn_gat_aggregate', C.byref(view), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
+                      F_.NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), int(relu), _stream())
+        ctx.rel, ctx.heads, ctx.relu, ctx.has_bias = rel, heads, relu, bias is not None
+        ctx.save_for_backward(H, ai, aj, rowmax, denom, out, bias)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        import ctypes as C
+        from . import _lib
+        from .graph import _ptr, _stream
+        H, ai, aj, rowmax, denom, out, bias = ctx.saved_tensors
+        rel, heads = ctx.rel, ctx.heads
+        feat = H.shape[1] // heads
+        dev = H.device
+        dout = F_._rows(dout)
+        if ctx.relu:
+            dout = F_.relu_backward_raw(dout, out)
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            db = torch.empty(heads * feat, dtype=torch.float32, device=dev)
+            F_.wgrad_raw(None, dout, 0, heads * feat, 0, None, db)
+        fwd, bwd = rel.fwd('rm'), rel.bwd('rm')
+        alpha_e = torch.empty(max(fwd.nnz, 1), heads, dtype=torch.float32, device=dev)
+        ds_e = torch.empty_like(alpha_e)
+        d_ai = torch.empty_like(ai)
+        d_aj = torch.empty_like(aj)
+        dH = torch.empty(H.shape[0], heads * feat, dtype=torch.float32, device=dev)
+        vf, vb = fwd.view(feat, heads), bwd.view(feat, heads)
+        perm = rel.bwd_to_fwd('rm')
+        with torch.cuda.device(dev):
+            _lib.call('peagnn_gat_backward_dst', C.byref(vf), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
+                      F_.NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), _ptr(dout),
+                      dout.stride(0), _ptr(alpha_e), _ptr(ds_e), _ptr(None), _ptr(None), _ptr(d_ai), _stream())
+            _lib.call('peagnn_gat_backward_src', C.byref(vb), _ptr(perm), _ptr(alpha_e), _ptr(ds_e), _ptr(None),
+                      _ptr(None), _ptr(dout), dout.stride(0), feat, heads, _ptr(dH), dH.stride(0), _ptr(d_aj), _stream())
+        return dH, d_ai, d_aj, db, None, None, None
+
+
+def shard_gat_aggregate(H, ai, aj, rel, heads, bias=None, relu=False):
+    return _ShardGatAggregate.apply(H, ai, aj, bias, rel, heads, relu)
 
 
 class _AllGatherRows(torch.autograd.Function):
@@ -219,11 +298,14 @@ class ShardedPropagation(object):
         self._rels = {}
         first = model.pea_channels[0].gnn_layers[0]
         tag = getattr(first, 'shares_aggregate', None)
-        if tag not in ('gcn', 'sage'):
-            raise NotImplementedError('row-sharded propagation covers the GCN and SAGE families; PEAGAT runs '
-                                      'replicated propagation with data-parallel batches')
+        if tag is None and hasattr(first, 'att_i'):
+            tag = 'gat'
+        if tag not in ('gcn', 'sage', 'gat'):
+            raise NotImplementedError('row-sharded propagation covers the PEAGCN / PEASage / PEAGAT families')
         self.kind = tag
         dev = model.x.device
+        rm_ids = plan.rank_major_to_global(dev)
+        self.rm_ids = rm_ids.clamp(min=0)                   # padding positions read node 0 (never gathered)
         own = plan.local_global_ids(device=dev)
         self.own_ids = own.clamp(min=0)
         self.own_valid = (own >= 0)
@@ -256,7 +338,67 @@ class ShardedPropagation(object):
             return 'rm', all_gather_rows(t, self.group)
         return layout, t
 
+    def _gat_gather(self, parts):
+        """One all-gather for a list of (H_local [rpr, HF], a_j_local [rpr, heads]) pairs; returns the
+        rank-major (H_full view, a_j_full) per pair."""
+        cols = [h for h, _ in parts] + [a for _, a in parts]       # feature blocks first: 16-byte aligned slices
+        width = sum(t.shape[1] for t in cols)
+        pad = (-width) % 4
+        if pad:
+            cols.append(cols[0].new_zeros(cols[0].shape[0], pad))
+        full = all_gather_rows(torch.cat(cols, dim=1), self.group)
+        out = []
+        off_h, off_a = 0, sum(h.shape[1] for h, _ in parts)
+        for h_loc, aj_loc in parts:
+            hf, hd = h_loc.shape[1], aj_loc.shape[1]
+            out.append((full[:, off_h:off_h + hf], full[:, off_a:off_a + hd].contiguous()))
+            off_h += hf
+            off_a += hd
+        return out
+
+    def _gat_channel_outputs(self):
+        model = self.model
+        plan, r = self.plan, self.plan.rank
+        rpr = plan.rows_per_rank
+        x_rm = model.x.index_select(0, self.rm_ids)            # embedding table in rank-major order, once
+        pending = []
+        for idx, channel in enumerate(model.pea_channels):
+            eil = model.meta_path_edge_index_list[idx]
+            assert len(eil) == channel.num_steps
+            local = None
+            for s, layer in enumerate(channel.gnn_layers):
+                if layer.training and layer.dropout > 0:
+                    raise NotImplementedError('attention dropout > 0 is not supported by the sm_100a GAT kernels')
+                rel = self.relation(eil[s])
+                last = s == channel.num_steps - 1
+                att_i, att_j = layer.att_i.view(-1), layer.att_j.view(-1)
+                if local is None:
+                    # first step: every rank projects the whole (replicated) table - cheaper than
+                    # gathering a [N, heads*hidden] table per metapath over NVLink
+                    h_full = F_.linear(x_rm, layer.lin.weight, None, w_is_out_in=True)
+                    ai_full, aj_full = F_.gat_scores(h_full, att_i, att_j, layer.heads)
+                    ai_loc = ai_full[r * rpr:(r + 1) * rpr]
+                else:
+                    h_loc = F_.linear(local, layer.lin.weight, None, w_is_out_in=True)
+                    ai_loc, aj_loc = F_.gat_scores(h_loc, att_i, att_j, layer.heads)
+                    if last:
+                        pending.append((layer, rel, h_loc, ai_loc, aj_loc))
+                        break
+                    (h_full, aj_full), = self._gat_gather([(h_loc, aj_loc)])
+                local = shard_gat_aggregate(h_full, ai_loc, aj_full, rel, layer.heads, layer.bias, relu=not last)
+            else:
+                pending.append(local)
+        todo = [k for k, o in enumerate(pending) if isinstance(o, tuple)]
+        if todo:
+            gathered = self._gat_gather([(pending[k][2], pending[k][4]) for k in todo])   # ONE all-gather
+            for k, (h_full, aj_full) in zip(todo, gathered):
+                layer, rel, _, ai_loc, _ = pending[k]
+                pending[k] = shard_gat_aggregate(h_full, ai_loc, aj_full, rel, layer.heads, layer.bias, relu=False)
+        return pending
+
     def channel_outputs(self):
+        if self.kind == 'gat':
+            return self._gat_channel_outputs()
         model = self.model
         shared, pending = {}, []
         for idx, channel in enumerate(model.pea_channels):

@@ -44,6 +44,7 @@ class Csr(object):
             heavy_threshold = min(HEAVY_THRESHOLD, SPARSE_HEAVY_THRESHOLD) if self.nnz < 8 * num_nodes else HEAVY_THRESHOLD
         self.heavy_threshold = heavy_threshold
         self.chunk_edges = CHUNK_EDGES if chunk_edges is None else chunk_edges
+        self.explicit_self_loops = False     # set by row shards that store self loops as edges
         self._build_work_list()
         self._partial = None
         self._views = {}
@@ -96,6 +97,7 @@ class Csr(object):
         v.col = self.col.data_ptr() if self.nnz else 0
         v.nrows = self.num_nodes
         v.nnz = self.nnz
+        v.explicit_self_loops = int(self.explicit_self_loops)
         v.row_offset = 0
         v.heavy_threshold = self.heavy_threshold
         v.n_heavy = self.n_heavy

@@ -85,6 +85,9 @@ typedef struct {
   float* partial;                 /* workspace, >= peagnn_partial_floats(...) floats          */
   int64_t nnz;                    /* edges of this view (scheduling hint: sparse views pack
                                      several rows per warp); 0 = unknown                      */
+  int32_t explicit_self_loops;    /* != 0: self loops are stored as ordinary edges of the view
+                                     (row shards); kernels then add no implicit self loop      */
+  int32_t reserved;
 } peagnn_csr_t;
 
 /* Floats of `partial` workspace an aggregation of width F (per head) needs on this view. */

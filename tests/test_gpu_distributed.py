@@ -67,7 +67,7 @@ def _worker(rank, world, port, kind, entity_aware, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('kind,entity_aware', [('gcn', False), ('sage', True)])
+@pytest.mark.parametrize('kind,entity_aware', [('gcn', False), ('sage', True), ('gat', False)])
 @pytest.mark.parametrize('world', [2, 3])
 def test_sharded_model_matches_unsharded(kind, entity_aware, world):
     mgr = mp.Manager()
@@ -81,12 +81,13 @@ def test_sharded_model_matches_unsharded(kind, entity_aware, world):
             assert e < 1e-4, (name, e)
 
 
-def test_gat_sharding_is_refused_loudly():
+def test_unknown_family_is_refused_loudly():
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from helpers import product_model_for
     from graph_recsys_benchmark_b200.datasets import SyntheticHIN
     from graph_recsys_benchmark_b200.distributed import shard_model
-    model = product_model_for(SyntheticHIN('tiny', seed=7), 'gat')
+    model = product_model_for(SyntheticHIN('tiny', seed=7), 'gcn')
+    model.pea_channels[0].gnn_layers[0] = torch.nn.Linear(4, 4).cuda()
     with pytest.raises(NotImplementedError):
         shard_model(model, 2, 0)
