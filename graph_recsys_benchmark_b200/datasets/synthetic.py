@@ -278,9 +278,30 @@ class SyntheticHIN(object):
         """(ptr[U+1], sorted item nids) of every item a user touched (train + held-out)."""
         uptr, items = self._all_user_items
         if self._train_items_sorted is None:
-            u = np.repeat(np.arange(self.num_uids), np.diff(uptr))
-            self._train_items_sorted = items[np.lexsort((items, u))]
+            u = np.repeat(np.arange(self.num_uids, dtype=np.int64), np.diff(uptr))
+            span = np.int64(self.type_accs['iid'] + self.num_iids + 1)
+            self._train_items_sorted = np.sort(u * span + items) % span
         return uptr, self._train_items_sorted
+
+    def unseen_counts(self):
+        """len(neg_unid_inid_map[u]) for every user, without building the lists."""
+        uptr, _ = self._all_user_items
+        return self.num_iids - np.diff(uptr)
+
+    def kth_unseen(self, idx):
+        """neg_unid_inid_map[u][idx[u, :]] for every user at once (the maps list unseen items in
+        ascending id order): the j-th missing id of a sorted list s is j + #{t : s_t - t <= j}."""
+        uptr, seen = self.user_seen_csr()
+        i0 = self.type_accs['iid']
+        U = self.num_uids
+        cnt = np.diff(uptr)
+        owner = np.repeat(np.arange(U, dtype=np.int64), cnt)
+        rank = np.arange(seen.shape[0], dtype=np.int64) - np.repeat(uptr[:-1], cnt)
+        big = np.int64(self.num_iids + 1)
+        key = (seen - i0 - rank) + owner * big                  # nondecreasing inside a user, users in order
+        q = idx.astype(np.int64) + np.arange(U, dtype=np.int64)[:, None] * big
+        below = np.searchsorted(key, q.ravel(), side='right').reshape(idx.shape) - uptr[:-1][:, None]
+        return idx + below + i0
 
     # ---- reference datasets/movielens.py:879-997 (BPR branch) ---------------------------------
     def cf_negative_sampling(self):

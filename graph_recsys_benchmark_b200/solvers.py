@@ -55,6 +55,19 @@ class BaseSolver(object):
         stream element by element in the same order.  Returns (users [U], cand [U, n_pos + num_neg])."""
         num_neg = self.train_args['num_neg_candidates']
         u_nids = list(dataset.test_pos_unid_inid_map.keys())
+        if hasattr(dataset, 'kth_unseen') and not isinstance(dataset.neg_unid_inid_map, dict):
+            # large graphs keep no per-user lists: same draws, pool[j] computed as the j-th unseen item
+            u0 = dataset.type_accs['uid']
+            if u_nids != list(range(u0, u0 + dataset.num_uids)):
+                raise NotImplementedError('lazy candidate pools need the users in node-id order')
+            pos = np.asarray([dataset.test_pos_unid_inid_map[u] for u in u_nids], dtype=np.int64)
+            n_pos = pos.shape[1]
+            sizes = dataset.unseen_counts()
+            if n_pos == 0 or (sizes <= 0).any():
+                raise ValueError("No pos or neg samples found in evaluation!")
+            idx = np.random.randint(0, sizes[:, None], size=(len(u_nids), num_neg))
+            cand = np.concatenate([pos, dataset.kth_unseen(idx)], axis=1)
+            return np.asarray(u_nids, dtype=np.int64), cand, n_pos
         pools = [dataset.neg_unid_inid_map[u] for u in u_nids]
         pos = [dataset.test_pos_unid_inid_map[u] for u in u_nids]
         n_pos = len(pos[0])
@@ -75,11 +88,21 @@ class BaseSolver(object):
         """reference solvers.py:33-104.  Returns (HR[16], NDCG[16], AUC[1], eval_loss[1]) as fp64
         numpy arrays (column means over users; index 5 is @10)."""
         device = self.train_args['device']
-        users, cand, n_pos = self.generate_all_candidates(dataset)
-        users_t = torch.from_numpy(users).to(device)
-        cand_t = torch.from_numpy(cand).to(device)
+        users, cand, n_pos = self.generate_all_candidates(dataset)     # identical draws on every rank
+        world, rank = 1, 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and not return_per_user:
+            world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        n_users = users.shape[0]
+        if world > 1:                                     # users are sharded; 36 partial sums are all-reduced
+            users, cand = users[rank::world], cand[rank::world]
+        users_t = torch.from_numpy(np.ascontiguousarray(users)).to(device)
+        cand_t = torch.from_numpy(np.ascontiguousarray(cand)).to(device)
         per_user, means, _ = F_.eval_rank(model.cached_repr, users_t, cand_t, n_pos, model.fc1.weight,
                                           model.fc1.bias, model.fc2.weight, model.fc2.bias)
+        if world > 1:
+            sums = means * float(users.shape[0])
+            torch.distributed.all_reduce(sums)
+            means = sums / float(n_users)
         m = means.cpu().numpy()                          # the only device->host read of an evaluation
         out = (m[0:16].copy(), m[16:32].copy(), m[32:33].copy(), m[33:34].copy())
         if return_per_user:

@@ -57,7 +57,18 @@ def _worker(rank, world, port, kind, entity_aware, ret):
 
         def rel(a, b):
             return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
+        # evaluation: users sharded over ranks + all-reduce of the partial sums == all users on one rank
+        from graph_recsys_benchmark_b200.solvers import BaseSolver
+        solver = BaseSolver(None, {}, {}, {'device': 'cuda', 'num_neg_candidates': 99, 'batch_size': 128})
+        model.eval()
+        np.random.seed(5)
+        hr_d, nd_d, auc_d, l_d = solver.metrics(1, 1, model, ds)
+        np.random.seed(5)
+        (hr_s, nd_s, auc_s, l_s), _ = solver.metrics(1, 1, model, ds, return_per_user=True)
+        eval_gap = max(float(np.abs(hr_d - hr_s).max()), float(np.abs(nd_d - nd_s).max()),
+                       float(np.abs(auc_d - auc_s).max()), float(np.abs(l_d - l_s).max() / abs(l_s[0])))
         ret[rank] = dict(
+            eval_gap=eval_gap,
             loss=abs(total.item() - loss_ref.item()) / abs(loss_ref.item()),
             repr=rel(model.cached_repr, ref_repr),
             grads={n: rel(p.grad, ref_grads[n]) for n, p in model.named_parameters()
@@ -76,6 +87,7 @@ def test_sharded_model_matches_unsharded(kind, entity_aware, world):
     for r in range(world):
         out = ret[r]
         assert out['loss'] < 1e-5, out
+        assert out['eval_gap'] < 1e-12, out
         assert out['repr'] < 1e-5, out
         for name, e in out['grads'].items():
             assert e < 1e-4, (name, e)

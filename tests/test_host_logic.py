@@ -173,3 +173,26 @@ def test_unsupported_options_raise(tiny):
         product_model_for(tiny, 'gcn', device='cpu', channel_aggr='att').__class__(**kw)
     with pytest.raises(AssertionError):
         product_model_for(tiny, 'gcn', device='cpu', steps=[2] * 8)
+
+
+def test_lazy_candidate_pools_draw_the_same_candidates():
+    """Large graphs keep no per-user negative lists; the j-th unseen item is computed instead.
+    Same numpy stream, same candidates as the dense-list path (and hence as the oracle)."""
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+    from graph_recsys_benchmark_b200.solvers import BaseSolver
+    dense = SyntheticHIN('tiny', seed=11)
+    lazy = SyntheticHIN('tiny', seed=11, dense_neg_map=False)
+    assert isinstance(dense.neg_unid_inid_map, dict) and not isinstance(lazy.neg_unid_inid_map, dict)
+    assert np.array_equal(lazy.unseen_counts(), np.array([len(dense.neg_unid_inid_map[u]) for u in range(dense.num_uids)]))
+    s = BaseSolver(None, {}, {}, {'device': 'cpu', 'num_neg_candidates': 99})
+    np.random.seed(7)
+    u1, c1, p1 = s.generate_all_candidates(dense)
+    st = np.random.get_state()[1].copy()
+    np.random.seed(7)
+    u2, c2, p2 = s.generate_all_candidates(lazy)
+    assert p1 == p2 == 1 and np.array_equal(u1, u2) and np.array_equal(c1, c2)
+    assert np.array_equal(np.random.get_state()[1], st)
+    full = np.arange(lazy.num_iids)[None, :].repeat(lazy.num_uids, 0)[:, :lazy.unseen_counts().min()]
+    got = lazy.kth_unseen(full)
+    for u in (0, 17, 39):
+        assert got[u].tolist() == dense.neg_unid_inid_map[u][:full.shape[1]]
