@@ -1,7 +1,7 @@
-"""PEASage + BPR - same command line as reference experiments/peasage_solver_bpr.py, e.g.
+"""PEASage + BPR with the reference's command line, e.g.
   python3 peasage_solver_bpr.py --dataset=Movielens --dataset_name=latest-small --sampling_strategy=unseen \
-      --entity_aware=false --emb_dim=64 --repr_dim=16 --hidden_size=64 --runs=1 --epochs=2 --batch_size=1024"""
-from pea_cli import run, models
+      --entity_aware=false --runs=1 --epochs=2 --batch_size=1024 --synthetic=ml-small"""
+from pea_cli import main
 
 if __name__ == '__main__':
-    run('PEASage', models.PEASageRecsysModel, with_heads=False)
+    main('PEASage')

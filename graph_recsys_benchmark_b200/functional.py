@@ -279,10 +279,18 @@ class _GatAggregate(torch.autograd.Function):
         denom = torch.empty_like(rowmax)
         out = torch.empty(n, heads * feat, dtype=torch.float32, device=dev)
         view = graph.fwd.view(feat, heads)
+        def launch():
+            with torch.cuda.device(dev):
+                _lib.call('peagnn_gat_aggregate', C.byref(view), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
+                          NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), int(relu), _stream())
         with torch.cuda.device(dev):
             _lib.call('peagnn_gat_rowmax', C.byref(view), _ptr(ai), _ptr(aj), heads, NEG_SLOPE, _ptr(rowmax), _stream())
-            _lib.call('peagnn_gat_aggregate', C.byref(view), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
-                      NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), int(relu), _stream())
+        if PROFILE is None:
+            launch()
+        else:      # E*(4 col + 4 a_j[src] + F*4) + N*(F*4 own row + 8 + F*4 write) + (N+1)*4, per head
+            nnz = graph.fwd.nnz
+            _timed('gat_f%d_e%d_n%d' % (feat, nnz, n),
+                   heads * (nnz * (8 + 4 * feat) + n * (8 * feat + 8) + (n + 1) * 4), launch)
         ctx.graph, ctx.heads, ctx.relu, ctx.has_bias = graph, heads, relu, bias is not None
         ctx.save_for_backward(H, ai, aj, rowmax, denom, out, bias)
         return out

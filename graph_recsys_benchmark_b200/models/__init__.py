@@ -1,10 +1,10 @@
 from .base import GraphRecsysModel, PEABaseChannel, PEABaseRecsysModel
-from .peagcn import PEAGCNChannel, PEAGCNRecsysModel
-from .peagat import PEAGATChannel, PEAGATRecsysModel
-from .peasage import PEASageChannel, PEASageRecsysModel
+from .families import (PEAChannel, channel_layer_dims,
+                       PEAGCNChannel, PEAGCNRecsysModel, PEAGATChannel, PEAGATRecsysModel,
+                       PEASageChannel, PEASageRecsysModel)
 
 __all__ = [
-    'GraphRecsysModel', 'PEABaseChannel', 'PEABaseRecsysModel',
+    'GraphRecsysModel', 'PEABaseChannel', 'PEABaseRecsysModel', 'PEAChannel', 'channel_layer_dims',
     'PEAGCNChannel', 'PEAGCNRecsysModel', 'PEAGATChannel', 'PEAGATRecsysModel',
     'PEASageChannel', 'PEASageRecsysModel',
 ]
