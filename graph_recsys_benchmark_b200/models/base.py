@@ -50,14 +50,12 @@ class GraphRecsysModel(torch.nn.Module):
 
     def eval(self, metapath_idx=None):
         """reference models/base.py:88-96: nn.Module.eval() + one no-grad propagation."""
-        super(GraphRecsysModel, self).eval()
-        if self.__class__.__name__ not in ['KGATRecsysModel', 'KGCNRecsysModel']:
-            if self.__class__.__name__[:3] == 'PEA':
-                with torch.no_grad():
-                    self.cached_repr = self.forward(metapath_idx)
-            else:
-                with torch.no_grad():
-                    self.cached_repr = self.forward()
+        torch.nn.Module.eval(self)
+        # upstream only forwards ``metapath_idx`` to classes whose NAME starts with 'PEA' (its PEASage
+        # script names the class MPASAGE..., silently disabling the ablation) - same rule here
+        ablate = metapath_idx if type(self).__name__.startswith('PEA') else None
+        with torch.no_grad():
+            self.cached_repr = self.forward() if ablate is None else self.forward(ablate)
         return self
 
 
@@ -101,49 +99,37 @@ class PEABaseRecsysModel(GraphRecsysModel):
         super(PEABaseRecsysModel, self).__init__(**kwargs)
 
     def _init(self, **kwargs):
-        self.entity_aware = kwargs['entity_aware']
-        self.entity_aware_coff = kwargs['entity_aware_coff']
-        self.meta_path_steps = kwargs['meta_path_steps']
-        self.if_use_features = kwargs['if_use_features']
-        self.channel_aggr = kwargs['channel_aggr']
-
-        # Create node embedding
-        if not self.if_use_features:
-            self.x = Parameter(torch.Tensor(kwargs['dataset']['num_nodes'], kwargs['emb_dim']))
-        else:
+        """Reads the reference's kwargs (models/base.py:148-179).  Module creation order is kept
+        (x, channels, att, fc1, fc2): it fixes both the state_dict key order of the shipped
+        checkpoints and the order in which the torch RNG is consumed at construction."""
+        for key in ('entity_aware', 'entity_aware_coff', 'meta_path_steps', 'if_use_features', 'channel_aggr'):
+            setattr(self, key, kwargs[key])
+        if self.if_use_features:
             raise NotImplementedError('Feature not implemented!')
+        steps, repr_dim = self.meta_path_steps, kwargs['repr_dim']
+        self.x = Parameter(torch.Tensor(kwargs['dataset']['num_nodes'], kwargs['emb_dim']))
 
-        # Create graphs (COO lists exactly as the reference keeps them; CSR is derived lazily)
-        meta_path_edge_index_list = self.update_graph_input(kwargs['dataset'])
-        assert len(meta_path_edge_index_list) == len(kwargs['meta_path_steps'])
-        self.meta_path_edge_index_list = meta_path_edge_index_list
+        # one COO list per (metapath, step), exactly as upstream keeps them; CSR is derived lazily
+        self.meta_path_edge_index_list = self.update_graph_input(kwargs['dataset'])
+        assert len(self.meta_path_edge_index_list) == len(steps)
 
-        # Create channels
-        self.pea_channels = torch.nn.ModuleList()
-        for num_steps in kwargs['meta_path_steps']:
-            kwargs_cpy = kwargs.copy()
-            kwargs_cpy['num_steps'] = num_steps
-            self.pea_channels.append(kwargs_cpy['channel_class'](**kwargs_cpy))
-
+        make_channel = kwargs['channel_class']
+        self.pea_channels = torch.nn.ModuleList(make_channel(**dict(kwargs, num_steps=s)) for s in steps)
         if self.channel_aggr == 'att':
-            self.att = Parameter(torch.Tensor(1, len(kwargs['meta_path_steps']), kwargs['repr_dim']))
-
-        if self.channel_aggr == 'cat':
-            self.fc1 = torch.nn.Linear(2 * len(kwargs['meta_path_steps']) * kwargs['repr_dim'], kwargs['repr_dim'])
-        else:
-            self.fc1 = torch.nn.Linear(2 * kwargs['repr_dim'], kwargs['repr_dim'])
-        self.fc2 = torch.nn.Linear(kwargs['repr_dim'], 1)
+            self.att = Parameter(torch.Tensor(1, len(steps), repr_dim))
+        fc1_in = 2 * repr_dim * (len(steps) if self.channel_aggr == 'cat' else 1)
+        self.fc1 = torch.nn.Linear(fc1_in, repr_dim)
+        self.fc2 = torch.nn.Linear(repr_dim, 1)
         self.cached_repr = None
 
     def reset_parameters(self):
-        if not self.if_use_features:
-            glorot(self.x)
-        for module in self.pea_channels:
-            module.reset_parameters()
-        glorot(self.fc1.weight)
-        glorot(self.fc2.weight)
-        if self.channel_aggr == 'att':
-            glorot(self.att)
+        """glorot on x, channel re-draws, glorot on fc1 / fc2 weights (biases keep nn.Linear's
+        init) and on att - the order of models/base.py:181-189."""
+        glorot(self.x)
+        for channel in self.pea_channels:
+            channel.reset_parameters()
+        for tensor in (self.fc1.weight, self.fc2.weight, getattr(self, 'att', None)):
+            glorot(tensor)
 
     batch_last_step = True     # one aggregation per distinct last-step relation (columns concatenated)
 
