@@ -45,7 +45,7 @@ SIGNATURES = {
     'peagnn_gat_backward_dst': (_INT, [_G, _P, _I64, _I32, _I32, _P, _P, _F, _P, _P, _P, _I64, _P, _P, _I64,
                                        _P, _P, _P, _P, _P, _P]),
     'peagnn_gat_backward_src': (_INT, [_G, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P]),
-    'peagnn_linear': (_INT, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _INT, _P, _INT, _INT, _P, _I64, _P]),
+    'peagnn_linear': (_INT, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _INT, _P, _INT, _INT, _P, _I64, _P, _I64, _P]),
     'peagnn_wgrad_workspace_floats': (_SZ, [_I64, _I32, _I32]),
     'peagnn_linear_wgrad': (_INT, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _I32, _INT, _P, _P, _P, _SZ, _P]),
     'peagnn_relu_backward': (_INT, [_P, _I64, _P, _I64, _I64, _I32, _P, _I64, _P]),
@@ -92,20 +92,24 @@ def last_error():
 
 
 profile = None      # when a list: every call appends (entry point, start event, end event)
+_fns = {}           # entry point name -> bound ctypes function
 
 
 def call(name, *args):
     """Invoke an int-returning entry point; raise on a non-zero code."""
     global launch_count
+    fn = _fns.get(name)
+    if fn is None:
+        fn = _fns[name] = getattr(load(), name)
     if profile is not None:
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        rc = getattr(load(), name)(*args)
+        rc = fn(*args)
         e1.record()
         profile.append((name, e0, e1))
     else:
-        rc = getattr(load(), name)(*args)
+        rc = fn(*args)
     launch_count += 1
     if rc != 0:
         raise RuntimeError('%s failed (%d): %s' % (name, rc, last_error()))

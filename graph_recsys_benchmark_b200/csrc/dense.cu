@@ -27,7 +27,8 @@ template <int TX>
 __global__ void __launch_bounds__(kLinThreads) linear_kernel(
     const float* __restrict__ X, int64_t ldx, const float* __restrict__ mask, int64_t ldm,
     int64_t n_rows, int K, int M, const float* __restrict__ W, int w_is_out_in,
-    const float* __restrict__ bias, int relu, int accumulate, float* __restrict__ Y, int64_t ldy) {
+    const float* __restrict__ bias, int relu, int accumulate, float* __restrict__ Y, int64_t ldy,
+    const float* __restrict__ out_mask, int64_t ldom) {
   constexpr int TY = kLinThreads / TX;
   constexpr int BM = TY * kRPT;
   extern __shared__ __align__(16) float smem[];
@@ -100,6 +101,10 @@ __global__ void __launch_bounds__(kLinThreads) linear_kernel(
             o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
           }
           if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (out_mask) {
+            const float4 g = ldg4(out_mask + row * ldom + 4 * tx);
+            o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
+          }
           st4(yp, o);
         }
       }
@@ -110,7 +115,8 @@ __global__ void __launch_bounds__(kLinThreads) linear_kernel(
 template <int TX>
 static int launch_linear(const float* X, int64_t ldx, const float* mask, int64_t ldm, int64_t n,
                          int K, int M, const float* W, int w_is_out_in, const float* bias, int relu,
-                         int accumulate, float* Y, int64_t ldy, cudaStream_t stream) {
+                         int accumulate, float* Y, int64_t ldy, const float* out_mask, int64_t ldom,
+                         cudaStream_t stream) {
   constexpr int TY = kLinThreads / TX;
   constexpr int BM = TY * kRPT;
   const size_t smem = ((size_t)K * M + (size_t)BM * (K + 4)) * sizeof(float);
@@ -123,7 +129,7 @@ static int launch_linear(const float* X, int64_t ldx, const float* mask, int64_t
   const int64_t tiles = (n + BM - 1) / BM;
   const int blocks = (int)imin64(tiles, (int64_t)kNumSMs * 4);
   linear_kernel<TX><<<blocks, kLinThreads, smem, stream>>>(X, ldx, mask, ldm, n, K, M, W, w_is_out_in,
-                                                           bias, relu, accumulate, Y, ldy);
+                                                           bias, relu, accumulate, Y, ldy, out_mask, ldom);
   return check_launch("peagnn_linear");
 }
 
@@ -438,19 +444,21 @@ using namespace peagnn;
 
 extern "C" int peagnn_linear(const float* X, int64_t ldx, const float* mask, int64_t ldm, int64_t n,
                              int32_t K, int32_t M, const float* W, int w_is_out_in, const float* bias,
-                             int relu, int accumulate, float* Y, int64_t ldy, peagnn_stream_t stream_) {
+                             int relu, int accumulate, float* Y, int64_t ldy, const float* out_mask,
+                             int64_t ldom, peagnn_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PEAGNN_REQUIRE(K > 0 && M > 0 && K % 4 == 0 && M % 4 == 0 && K <= 128 && M <= 128,
                  "peagnn_linear: K=%d, M=%d must be multiples of 4 in [4, 128]", K, M);
   PEAGNN_REQUIRE(X && W && Y && ldx % 4 == 0 && ldy % 4 == 0 && ldx >= K && ldy >= M && (!mask || (ldm % 4 == 0 && ldm >= K)),
                  "peagnn_linear: bad pointers / leading dimensions");
-  PEAGNN_REQUIRE(aligned16(X) && aligned16(Y) && (!mask || aligned16(mask)) && (!bias || aligned16(bias)),
+  PEAGNN_REQUIRE(aligned16(X) && aligned16(Y) && (!mask || aligned16(mask)) && (!bias || aligned16(bias)) &&
+                     (!out_mask || (aligned16(out_mask) && ldom % 4 == 0 && ldom >= M)),
                  "peagnn_linear: pointers must be 16-byte aligned");
   if (n == 0) return PEAGNN_OK;
   const int tx = pow2_ge(M / 4);
   if ((K == 64 || K == 16) && tx <= 16) {   // hot shapes: prefetching register-tile kernels
 #define PEAGNN_LIN2(K_, TX_, RPT_) \
-  return launch_linear_v2<K_, TX_, RPT_>(X, ldx, mask, ldm, n, M, W, w_is_out_in, bias, relu, accumulate, Y, ldy, stream)
+  return launch_linear_v2<K_, TX_, RPT_>(X, ldx, mask, ldm, n, M, W, w_is_out_in, bias, relu, accumulate, Y, ldy, out_mask, ldom, stream)
     if (K == 64) {
       if (tx <= 4) PEAGNN_LIN2(64, 4, 2);
       if (tx == 8) PEAGNN_LIN2(64, 8, 4);
@@ -463,7 +471,7 @@ extern "C" int peagnn_linear(const float* X, int64_t ldx, const float* mask, int
 #undef PEAGNN_LIN2
   }
 #define PEAGNN_LIN_CASE(TX_) \
-  return launch_linear<TX_>(X, ldx, mask, ldm, n, K, M, W, w_is_out_in, bias, relu, accumulate, Y, ldy, stream)
+  return launch_linear<TX_>(X, ldx, mask, ldm, n, K, M, W, w_is_out_in, bias, relu, accumulate, Y, ldy, out_mask, ldom, stream)
   if (tx <= 4) PEAGNN_LIN_CASE(4);
   if (tx == 8) PEAGNN_LIN_CASE(8);
   if (tx == 16) PEAGNN_LIN_CASE(16);

@@ -17,7 +17,8 @@ template <int K, int TX, int RPT, bool HAS_MASK>
 __global__ void __launch_bounds__(kV2Threads) linear_v2_kernel(
     const float* __restrict__ X, int64_t ldx, const float* __restrict__ mask, int64_t ldm,
     int64_t n_rows, int M, const float* __restrict__ W, int w_is_out_in,
-    const float* __restrict__ bias, int relu, int accumulate, float* __restrict__ Y, int64_t ldy) {
+    const float* __restrict__ bias, int relu, int accumulate, float* __restrict__ Y, int64_t ldy,
+    const float* __restrict__ out_mask, int64_t ldom) {
   constexpr int TY = kV2Threads / TX;
   constexpr int BM = TY * RPT;
   constexpr int K4 = K / 4;
@@ -119,6 +120,10 @@ __global__ void __launch_bounds__(kV2Threads) linear_v2_kernel(
             o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
           }
           if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (out_mask) {   // relu backward fused on the way out: keep the gradient where the activation was > 0
+            const float4 g = ldg4(out_mask + row * ldom + 4 * tx);
+            o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
+          }
           st4(yp, o);
         }
       }
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(kV2Threads) linear_v2_kernel(
 template <int K, int TX, int RPT>
 static int launch_linear_v2(const float* X, int64_t ldx, const float* mask, int64_t ldm, int64_t n, int M,
                             const float* W, int w_is_out_in, const float* bias, int relu, int accumulate,
-                            float* Y, int64_t ldy, cudaStream_t stream) {
+                            float* Y, int64_t ldy, const float* out_mask, int64_t ldom, cudaStream_t stream) {
   constexpr int TY = kV2Threads / TX;
   constexpr int BM = TY * RPT;
   const size_t smem = ((size_t)K * 4 * TX + (size_t)BM * (K + 4)) * sizeof(float);
@@ -143,10 +148,10 @@ static int launch_linear_v2(const float* X, int64_t ldx, const float* mask, int6
   const int blocks = (int)imin64(tiles, (int64_t)kNumSMs * 2);
   if (mask)
     linear_v2_kernel<K, TX, RPT, true><<<blocks, kV2Threads, smem, stream>>>(X, ldx, mask, ldm, n, M, W, w_is_out_in,
-                                                                            bias, relu, accumulate, Y, ldy);
+                                                                            bias, relu, accumulate, Y, ldy, out_mask, ldom);
   else
     linear_v2_kernel<K, TX, RPT, false><<<blocks, kV2Threads, smem, stream>>>(X, ldx, mask, ldm, n, M, W, w_is_out_in,
-                                                                             bias, relu, accumulate, Y, ldy);
+                                                                             bias, relu, accumulate, Y, ldy, out_mask, ldom);
   return check_launch("peagnn_linear(v2)");
 }
 

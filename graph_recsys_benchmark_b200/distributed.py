@@ -193,7 +193,7 @@ class _ShardGatAggregate(torch.autograd.Function):
         denom = torch.empty_like(rowmax)
         out = torch.empty(rpr, heads * feat, dtype=torch.float32, device=dev)
         view = rel.fwd('rm').view(feat, heads)
-        with torch.cuda.device(dev):
+        with F_._on(dev):
             _lib.call('peagnn_gat_rowmax', C.byref(view), _ptr(ai), _ptr(aj), heads, F_.NEG_SLOPE, _ptr(rowmax), _stream())
             _lib.call('peagnn_gat_aggregate', C.byref(view), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
                       F_.NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), int(relu), _stream())
@@ -225,7 +225,7 @@ class _ShardGatAggregate(torch.autograd.Function):
         dH = torch.empty(H.shape[0], heads * feat, dtype=torch.float32, device=dev)
         vf, vb = fwd.view(feat, heads), bwd.view(feat, heads)
         perm = rel.bwd_to_fwd('rm')
-        with torch.cuda.device(dev):
+        with F_._on(dev):
             _lib.call('peagnn_gat_backward_dst', C.byref(vf), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
                       F_.NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), _ptr(dout),
                       dout.stride(0), _ptr(alpha_e), _ptr(ds_e), _ptr(None), _ptr(None), _ptr(d_ai), _stream())

@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .graph import _ptr, _stream
+from .graph import _ptr, _stream, _on
 
 NEG_SLOPE = 0.2
 
@@ -64,7 +64,7 @@ def spmm_raw(csr, X, feat, out, rs=None, cs=None, self_loop=False, bias=None, re
     view = csr.view(feat)
 
     def launch():
-        with torch.cuda.device(X.device):
+        with _on(X.device):
             _lib.call('peagnn_spmm', C.byref(view), _ptr(X), X.stride(0), feat, _ptr(out), out.stride(0),
                       _ptr(rs), _ptr(cs), int(self_loop), _ptr(bias), int(relu), int(accumulate), _stream())
     if PROFILE is None:
@@ -77,13 +77,14 @@ def spmm_raw(csr, X, feat, out, rs=None, cs=None, self_loop=False, bias=None, re
     return out
 
 
-def linear_raw(X, W, out, w_is_out_in, bias=None, relu=False, accumulate=False, mask=None):
+def linear_raw(X, W, out, w_is_out_in, bias=None, relu=False, accumulate=False, mask=None, out_mask=None):
     n, K = X.shape
     M = out.shape[1]
-    with torch.cuda.device(X.device):
+    with _on(X.device):
         _lib.call('peagnn_linear', _ptr(X), X.stride(0), _ptr(mask), mask.stride(0) if mask is not None else 0,
                   n, K, M, _ptr(W), int(w_is_out_in), _ptr(bias), int(relu), int(accumulate),
-                  _ptr(out), out.stride(0), _stream())
+                  _ptr(out), out.stride(0), _ptr(out_mask), out_mask.stride(0) if out_mask is not None else 0,
+                  _stream())
     return out
 
 
@@ -91,7 +92,7 @@ def wgrad_raw(X, dY, K, M, w_is_out_in, dW, db, mask=None):
     n = dY.shape[0]
     need = int(_lib.query('peagnn_wgrad_workspace_floats', n, K, M))
     ws = _ws(need, dY.device)
-    with torch.cuda.device(dY.device):
+    with _on(dY.device):
         _lib.call('peagnn_linear_wgrad', _ptr(X), X.stride(0) if X is not None else 0, _ptr(dY), dY.stride(0),
                   _ptr(mask), mask.stride(0) if mask is not None else 0, n, K, M, int(w_is_out_in),
                   _ptr(dW), _ptr(db), _ptr(ws), need, _stream())
@@ -99,7 +100,7 @@ def wgrad_raw(X, dY, K, M, w_is_out_in, dW, db, mask=None):
 
 def relu_backward_raw(dy, act):
     out = torch.empty_like(act)
-    with torch.cuda.device(dy.device):
+    with _on(dy.device):
         _lib.call('peagnn_relu_backward', _ptr(dy), dy.stride(0), _ptr(act), act.stride(0), dy.shape[0],
                   dy.shape[1], _ptr(out), out.stride(0), _stream())
     return out
@@ -242,7 +243,7 @@ class _GatScores(torch.autograd.Function):
         ai = torch.empty(n, heads, dtype=torch.float32, device=H.device)
         aj = torch.empty_like(ai)
         att_i, att_j = att_i.contiguous(), att_j.contiguous()
-        with torch.cuda.device(H.device):
+        with _on(H.device):
             _lib.call('peagnn_gat_scores', _ptr(H), H.stride(0), n, feat, heads, _ptr(att_i), _ptr(att_j),
                       _ptr(ai), _ptr(aj), _stream())
         ctx.heads = heads
@@ -260,7 +261,7 @@ class _GatScores(torch.autograd.Function):
         d_att_i, d_att_j = torch.empty_like(att_i), torch.empty_like(att_j)
         need = int(_lib.query('peagnn_wgrad_workspace_floats', n, heads * feat, 4))
         ws = _ws(need, H.device)
-        with torch.cuda.device(H.device):
+        with _on(H.device):
             _lib.call('peagnn_gat_scores_backward', _ptr(H), H.stride(0), n, feat, heads, _ptr(att_i), _ptr(att_j),
                       _ptr(d_ai), _ptr(d_aj), _ptr(dH), dH.stride(0), 0, _ptr(d_att_i), _ptr(d_att_j),
                       _ptr(ws), need, _stream())
@@ -280,10 +281,10 @@ class _GatAggregate(torch.autograd.Function):
         out = torch.empty(n, heads * feat, dtype=torch.float32, device=dev)
         view = graph.fwd.view(feat, heads)
         def launch():
-            with torch.cuda.device(dev):
+            with _on(dev):
                 _lib.call('peagnn_gat_aggregate', C.byref(view), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
                           NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), int(relu), _stream())
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.call('peagnn_gat_rowmax', C.byref(view), _ptr(ai), _ptr(aj), heads, NEG_SLOPE, _ptr(rowmax), _stream())
         if PROFILE is None:
             launch()
@@ -322,7 +323,7 @@ class _GatAggregate(torch.autograd.Function):
         vf = graph.fwd.view(feat, heads)
         vb = graph.bwd.view(feat, heads)
         perm = graph.bwd_to_fwd
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.call('peagnn_gat_backward_dst', C.byref(vf), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
                       NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), _ptr(dout), dout.stride(0),
                       _ptr(alpha_e), _ptr(ds_e), _ptr(alpha_s), _ptr(ds_s), _ptr(d_ai), _stream())
@@ -351,7 +352,7 @@ class _Fuse(torch.autograd.Function):
         n, P, D = Z.shape
         out = torch.empty(n, D, dtype=torch.float32, device=Z.device)
         att2 = att.reshape(P, D).contiguous() if att is not None else None
-        with torch.cuda.device(Z.device):
+        with _on(Z.device):
             _lib.call('peagnn_fuse_forward', _ptr(Z), P * D, n, P, D, _ptr(att2), mode, skip, _ptr(out), D, _stream())
         ctx.mode, ctx.skip = mode, skip
         ctx.att_shape = att.shape if att is not None else None
@@ -369,7 +370,7 @@ class _Fuse(torch.autograd.Function):
         d_att = torch.empty(P, D, dtype=torch.float32, device=Z.device) if ctx.mode == 0 else None
         need = int(_lib.query('peagnn_fuse_workspace_floats', n, P, D)) if ctx.mode == 0 else 0
         ws = _ws(need, Z.device) if ctx.mode == 0 else None
-        with torch.cuda.device(Z.device):
+        with _on(Z.device):
             _lib.call('peagnn_fuse_backward', _ptr(Z), P * D, n, P, D, _ptr(att2), ctx.mode, _ptr(dout), dout.stride(0),
                       _ptr(dZ), P * D, _ptr(d_att), _ptr(ws), need, _stream())
         return dZ, (d_att.reshape(ctx.att_shape) if d_att is not None else None), None, None
@@ -389,7 +390,7 @@ def predict_raw(repr_, unids, inids, fc1_w, fc1_b, fc2_w, fc2_b):
         raise TypeError('node ids must be int64 (torch.long)')
     B = int(unids.numel())
     out = torch.empty(B, 1, dtype=torch.float32, device=repr_.device)
-    with torch.cuda.device(repr_.device):
+    with _on(repr_.device):
         _lib.call('peagnn_predict', _ptr(repr_), repr_.stride(0), repr_.shape[1], _ptr(unids), _ptr(inids), B,
                   _ptr(fc1_w.contiguous()), _ptr(fc1_b.contiguous()), _ptr(fc2_w.contiguous()), _ptr(fc2_b.contiguous()),
                   _ptr(out), _stream())
@@ -429,7 +430,7 @@ class _BprLoss(torch.autograd.Function):
             g1w, g1b, g2w, g2b = (torch.empty_like(t) for t in (fc1_w, fc1_b, fc2_w, fc2_b))
         else:
             d_repr = g1w = g1b = g2w = g2b = None
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.call('peagnn_bpr_loss', _ptr(repr_), repr_.stride(0), D, _ptr(batch), cols, B,
                       _ptr(fc1_w), _ptr(fc1_b), _ptr(fc2_w), _ptr(fc2_b), _ptr(loss), int(need_grad),
                       _ptr(d_repr), d_repr.stride(0) if need_grad else 0, _ptr(g1w), _ptr(g1b), _ptr(g2w), _ptr(g2b),
@@ -457,7 +458,7 @@ class _EntityReg(torch.autograd.Function):
         loss = torch.zeros(1, dtype=torch.float32, device=dev)
         dx = torch.zeros_like(x) if need_grad else None
         ws = _ws(B, dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _lib.call('peagnn_entity_reg', _ptr(x), x.stride(0), x.shape[1], _ptr(batch), B, float(coff), _ptr(loss),
                       int(need_grad), _ptr(dx), dx.stride(0) if need_grad else 0, _ptr(ws), B, _stream())
         if need_grad:
@@ -493,7 +494,7 @@ def eval_rank(repr_, users, cand, n_pos, fc1_w, fc1_b, fc2_w, fc2_b, return_scor
     scores = torch.empty(U, Cn, dtype=torch.float32, device=dev) if return_scores else None
     means = torch.empty(36, dtype=torch.float64, device=dev)
     ws = torch.empty(148 * 36, dtype=torch.float64, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.call('peagnn_eval_rank', _ptr(repr_), repr_.stride(0), repr_.shape[1], _ptr(users), _ptr(cand), U, Cn,
                   int(n_pos), _ptr(fc1_w.contiguous()), _ptr(fc1_b.contiguous()), _ptr(fc2_w.contiguous()),
                   _ptr(fc2_b.contiguous()), _ptr(per_user), _ptr(scores), _stream())

@@ -33,6 +33,27 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _Here(object):
+    """No-op context: the tensor's device is already current (the common case - switching the
+    device around every launch costs more host time than the launch itself)."""
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_HERE = _Here()
+
+
+def _on(device):
+    """Context that makes ``device`` current for a launch."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _HERE
+    return torch.cuda.device(device)
+
+
 class Csr(object):
     """One CSR structure (rows gather from ``col``) plus its heavy-row work list."""
 
@@ -90,9 +111,14 @@ class Csr(object):
         return self._partial
 
     def view(self, feat, heads=1):
-        """``peagnn_csr_t`` for the whole structure (ctypes struct; keeps tensors alive via self)."""
+        """``peagnn_csr_t`` for the whole structure (ctypes struct; keeps tensors alive via self).
+        Cached per (feat, heads): the struct only changes when the partial workspace is regrown."""
         part = self.partial(feat, heads)
-        v = _lib.CsrView()
+        key = (feat, heads, part.data_ptr() if part is not None else 0, self.explicit_self_loops)
+        hit = self._views.get(key)
+        if hit is not None:
+            return hit
+        v = self._views[key] = _lib.CsrView()
         v.rowptr = self.rowptr.data_ptr()
         v.col = self.col.data_ptr() if self.nnz else 0
         v.nrows = self.num_nodes
@@ -175,7 +201,7 @@ def build_csr(key, val, num_nodes, drop_self_loops=True, heavy_threshold=None, c
     eid = torch.empty(E, dtype=torch.int32, device=dev)
     ws_bytes = int(_lib.query('peagnn_csr_workspace_bytes', E, num_nodes))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.call('peagnn_csr_build', _ptr(key), _ptr(val), E, num_nodes, int(drop_self_loops),
                   _ptr(rowptr), _ptr(col), _ptr(eid), _ptr(ws), ws_bytes, _stream())
         kept = int(rowptr[-1].item())       # one-off sync at graph-build time
@@ -220,7 +246,7 @@ class RelationGraph(object):
 
     def _scale(self, csr, add, power, clamp):
         out = torch.empty(self.num_nodes, dtype=torch.float32, device=csr.rowptr.device)
-        with torch.cuda.device(out.device):
+        with _on(out.device):
             _lib.call('peagnn_degree_scale', _ptr(csr.rowptr), self.num_nodes, float(add), float(power),
                       int(clamp), _ptr(out), _stream())
         return out

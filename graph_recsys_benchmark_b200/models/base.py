@@ -132,6 +132,7 @@ class PEABaseRecsysModel(GraphRecsysModel):
             glorot(tensor)
 
     batch_last_step = True     # one aggregation per distinct last-step relation (columns concatenated)
+    fused_engine = True        # engine.py: head / body autograd nodes instead of one node per kernel
 
     def channel_outputs(self):
         x = self.x
@@ -163,6 +164,14 @@ class PEABaseRecsysModel(GraphRecsysModel):
             raise NotImplementedError('Other aggr methods not implemeted!')
         if getattr(self, '_sharded', None) is not None:      # distributed.shard_model(): row-sharded propagation
             return self._sharded.forward(metapath_idx)
+        if self.fused_engine:                                # whole-model schedule for the standard PEAGCN shape
+            ok = getattr(self, '_engine_ok', None)
+            if ok is None:
+                from ..engine import GcnPlan
+                ok = self._engine_ok = GcnPlan.applies(self)
+            if ok:
+                from ..engine import gcn_forward
+                return gcn_forward(self, metapath_idx)
         z = torch.stack(self.channel_outputs(), dim=1)                  # [N, P, repr]
         att = self.att if self.channel_aggr == 'att' else None
         return F_.fuse_channels(z, att, self.channel_aggr, metapath_idx)

@@ -144,11 +144,14 @@ int peagnn_gat_backward_src(const peagnn_csr_t* gt, const int32_t* perm, const f
  * K4: node-wise projections (the matmul / nn.Linear inside each conv; fc1/fc2 are in K6).
  *   Y[n,:] = act( X[n,:] @ W (+ bias) ) (+ Y if accumulate);  W is [K, M] row-major, or
  *   [M, K] row-major (nn.Linear layout) when w_is_out_in != 0.   K, M multiples of 4, <= 128.
- * If mask != NULL the input is gated on load: X[n,k] * (mask[n,k] > 0)  (relu backward).
+ *   accumulate adds the previous contents of Y before the activation.
+ * If mask != NULL the input is gated on load: X[n,k] * (mask[n,k] > 0); if out_mask != NULL the
+ * OUTPUT is gated on store: Y[n,m] * (out_mask[n,m] > 0) - both are relu-backward fusions.
  * ---------------------------------------------------------------------------------------- */
 int peagnn_linear(const float* X, int64_t ldx, const float* mask, int64_t ldm, int64_t num_rows,
                   int32_t K, int32_t M, const float* W, int w_is_out_in, const float* bias,
-                  int relu, int accumulate, float* Y, int64_t ldy, peagnn_stream_t stream);
+                  int relu, int accumulate, float* Y, int64_t ldy, const float* out_mask,
+                  int64_t ldom, peagnn_stream_t stream);
 
 /* Floats of workspace for peagnn_linear_wgrad. */
 size_t peagnn_wgrad_workspace_floats(int64_t num_rows, int32_t K, int32_t M);

@@ -66,7 +66,7 @@ def test_argument_errors_are_reported_not_crashed(lib):
     rc = lib.peagnn_spmm(ctypes.byref(v), None, 64, 63, None, 64, None, None, 0, None, 0, 0, None)
     assert rc < 0 and b'peagnn_spmm' in lib.peagnn_last_error()
     with pytest.raises(RuntimeError):
-        _lib.call('peagnn_linear', None, 64, None, 0, 10, 63, 64, None, 0, None, 0, 0, None, 64, None)
+        _lib.call('peagnn_linear', None, 64, None, 0, 10, 63, 64, None, 0, None, 0, 0, None, 64, None, 0, None)
 
 
 def test_missing_library_fails_loudly(monkeypatch):

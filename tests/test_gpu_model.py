@@ -149,3 +149,48 @@ def test_experiment_cli_trains_evaluates_checkpoints_and_resumes(tmp_path, monke
     pea_cli.run('PEAGCN', models.PEAGCNRecsysModel, argv=[a if not a.startswith('--epochs') else '--epochs=3' for a in argv])
     out = capsys.readouterr().out
     assert "Loaded checkpoint_backup" in out and 'Run: 1, epoch: 3, HR@5' in out and 'Run: 1, epoch: 2, HR@5' not in out
+
+
+@pytest.mark.parametrize('aggr', ['att', 'mean'])
+@pytest.mark.parametrize('entity_aware', [False, True])
+def test_fused_engine_equals_layer_path(aggr, entity_aware):
+    """engine.py (two autograd nodes, planned buffers) and the per-layer modules run the same
+    kernels: loss, representation and every gradient agree to rounding."""
+    from graph_recsys_benchmark_b200.engine import GcnPlan
+    ds = _dataset()
+    batch = _batch(ds, 300, entity_aware).to(DEV)
+    torch.manual_seed(11)
+    model = product_model_for(ds, 'gcn', entity_aware=entity_aware, channel_aggr=aggr)
+    assert GcnPlan.applies(model)
+    model.train()
+    res = {}
+    for fused in (True, False):
+        model.fused_engine = fused
+        model.zero_grad()
+        loss = model.loss(batch)
+        loss.backward()
+        res[fused] = (loss.item(), model.cached_repr.detach().clone(),
+                      {n: p.grad.clone() for n, p in model.named_parameters()})
+    assert abs(res[True][0] - res[False][0]) <= 1e-6 * abs(res[False][0])
+    assert rel_err(res[True][1], res[False][1]) < 1e-6
+    for n, g in res[False][2].items():
+        if float(g.abs().max()) > 1e-12:
+            assert rel_err(res[True][2][n], g) < 1e-5, n
+    for idx in (0, 4):                                   # ablation goes through the engine too
+        outs = []
+        for fused in (True, False):
+            model.fused_engine = fused
+            model.eval(idx)
+            outs.append(model.cached_repr.clone())
+        assert rel_err(outs[0], outs[1]) < 1e-6
+
+
+def test_engine_declines_other_shapes():
+    from graph_recsys_benchmark_b200.engine import GcnPlan
+    ds = _dataset()
+    assert not GcnPlan.applies(product_model_for(ds, 'sage'))
+    assert not GcnPlan.applies(product_model_for(ds, 'gat'))
+    assert not GcnPlan.applies(product_model_for(ds, 'gcn', steps=[2, 2, 1, 2, 2, 2, 2, 2, 2]))
+    m = product_model_for(ds, 'gcn', steps=[2, 2, 3, 2, 2, 2, 2, 2, 2])      # falls back to the layer path
+    m.eval()
+    assert m.cached_repr.shape == (ds.num_nodes, 16)
