@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument('--model', default='gcn', choices=['gcn', 'gat', 'sage'])
     ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--breakdown', action='store_true', help='extra untimed pass: ms per C-ABI entry point')
     ap.add_argument('--prewarm', type=float, default=2.0, help='seconds of untimed steps before the warm-up')
     return ap.parse_args()
 
@@ -293,13 +294,15 @@ def run_product(args):
     ms_e2e = t_e2e[0].elapsed_time(t_e2e[1])
 
     # ---- untimed extra pass: per-entry-point breakdown (events around every C-ABI call) --------
-    _lib.profile = []
-    for k in range(min(K, 5)):
-        step(dev_batches[W + k])
-    barrier()
-    prof_all = _lib.profile
-    _lib.profile = None
-    K_prof = min(K, 5)
+    prof_all, K_prof = [], 1
+    if args.breakdown:
+        K_prof = min(K, 5)
+        _lib.profile = []
+        for k in range(K_prof):
+            step(dev_batches[W + k])
+        barrier()
+        prof_all = _lib.profile
+        _lib.profile = None
 
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -358,9 +361,10 @@ def run_product(args):
                          'launches_per_step': len(prof_spmm) / K if prof_spmm else None,
                          'ms_per_step': agg_ms / K,
                          'share_of_step': agg_ms / ms_total if ms_total > 0 else None},
-            'breakdown_ms_per_step': breakdown,
             'clocks': clocks.summary(),
         }
+        if args.breakdown:
+            line['breakdown_ms_per_step'] = breakdown
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             t_lite, ds_lite, _ = cpu_oracle_steps(args.workload, args.model, B, 1, 1 if LITE.get(args.workload) != 'ml-25m-lite' else 0, threads)

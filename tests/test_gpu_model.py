@@ -190,7 +190,7 @@ def test_engine_declines_other_shapes():
     ds = _dataset()
     assert not GcnPlan.applies(product_model_for(ds, 'sage'))
     assert not GcnPlan.applies(product_model_for(ds, 'gat'))
-    assert not GcnPlan.applies(product_model_for(ds, 'gcn', steps=[2, 2, 1, 2, 2, 2, 2, 2, 2]))
-    m = product_model_for(ds, 'gcn', steps=[2, 2, 3, 2, 2, 2, 2, 2, 2])      # falls back to the layer path
-    m.eval()
-    assert m.cached_repr.shape == (ds.num_nodes, 16)
+    m = product_model_for(ds, 'gcn', hidden=16)          # hidden == repr: both steps aggregate first
+    assert not GcnPlan.applies(m)
+    m.eval()                                             # ... and the per-layer path serves it
+    assert m.cached_repr.shape == (ds.num_nodes, 16) and bool(torch.isfinite(m.cached_repr).all())
