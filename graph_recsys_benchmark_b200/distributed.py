@@ -238,6 +238,34 @@ def shard_gat_aggregate(H, ai, aj, rel, heads, bias=None, relu=False):
     return _ShardGatAggregate.apply(H, ai, aj, bias, rel, heads, relu)
 
 
+def raw_all_gather(local, group=None):
+    """[rows_per_rank, F] -> [R * rows_per_rank, F] (rank-major).  NCCL all_gather_into_tensor; gloo
+    (CPU / single-GPU test rigs) goes through the list form."""
+    local = local.contiguous()
+    world = dist.get_world_size(group)
+    out = torch.empty(world * local.shape[0], local.shape[1], dtype=local.dtype, device=local.device)
+    if dist.get_backend(group) == 'gloo':
+        dist.all_gather(list(out.chunk(world, dim=0)), local, group=group)
+    else:
+        dist.all_gather_into_tensor(out, local, group=group)
+    return out
+
+
+def raw_reduce_scatter(full, group=None):
+    """Sum over ranks of [R * rows_per_rank, F], each rank keeping its own row block."""
+    full = full.contiguous()
+    world = dist.get_world_size(group)
+    rows = full.shape[0] // world
+    if dist.get_backend(group) == 'gloo':               # gloo has no reduce-scatter: all-reduce, keep own slice
+        full = full.clone()
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+        r = dist.get_rank(group)
+        return full[r * rows:(r + 1) * rows].contiguous()
+    local = torch.empty(rows, full.shape[1], dtype=full.dtype, device=full.device)
+    dist.reduce_scatter_tensor(local, full, op=dist.ReduceOp.SUM, group=group)
+    return local
+
+
 class _AllGatherRows(torch.autograd.Function):
     """[rows_per_rank, F] per rank -> [R * rows_per_rank, F] rank-major on every rank.
     Backward: every rank holds a gradient for the whole table; the owner needs their sum ->
@@ -245,29 +273,12 @@ class _AllGatherRows(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, local, group):
-        local = local.contiguous()
-        world = dist.get_world_size(group)
-        out = torch.empty(world * local.shape[0], local.shape[1], dtype=local.dtype, device=local.device)
-        if dist.get_backend(group) == 'gloo':           # CPU / single-GPU test rigs
-            dist.all_gather(list(out.chunk(world, dim=0)), local, group=group)
-        else:
-            dist.all_gather_into_tensor(out, local, group=group)
         ctx.group = group
-        return out
+        return raw_all_gather(local, group)
 
     @staticmethod
     def backward(ctx, dfull):
-        dfull = dfull.contiguous()
-        world = dist.get_world_size(ctx.group)
-        rows = dfull.shape[0] // world
-        if dist.get_backend(ctx.group) == 'gloo':       # gloo has no reduce-scatter: all-reduce, keep own slice
-            dfull = dfull.clone()
-            dist.all_reduce(dfull, op=dist.ReduceOp.SUM, group=ctx.group)
-            r = dist.get_rank(ctx.group)
-            return dfull[r * rows:(r + 1) * rows].contiguous(), None
-        dlocal = torch.empty(rows, dfull.shape[1], dtype=dfull.dtype, device=dfull.device)
-        dist.reduce_scatter_tensor(dlocal, dfull, op=dist.ReduceOp.SUM, group=ctx.group)
-        return dlocal, None
+        return raw_reduce_scatter(dfull, ctx.group), None
 
 
 def all_gather_rows(local, group=None):
@@ -310,6 +321,13 @@ class ShardedPropagation(object):
         self.own_ids = own.clamp(min=0)
         self.own_valid = (own >= 0)
         self.rm_of_global = plan.to_rank_major(torch.arange(plan.num_nodes, device=dev))
+        self._plan, self._applies = None, None
+
+    def _engine_applies(self):
+        if self._applies is None:
+            from .engine import GcnPlan
+            self._applies = GcnPlan.applies(self.model)
+        return self._applies
 
     def relation(self, edge_index):
         key = (edge_index.data_ptr(), int(edge_index.shape[1]))
@@ -454,11 +472,87 @@ class ShardedPropagation(object):
 
     def forward(self, metapath_idx=None):
         model = self.model
-        z = torch.stack(self.channel_outputs(), dim=1)                 # [rows_per_rank, P, repr]
-        att = model.att if model.channel_aggr == 'att' else None
-        fused_local = F_.fuse_channels(z, att, model.channel_aggr, metapath_idx)
+        if self.kind == 'gcn' and model.fused_engine and self._engine_applies():
+            from .engine import gcn_forward
+            if self._plan is None:
+                self._plan = ShardedGcnPlan(model, self)
+            fused_local = gcn_forward(model, metapath_idx, plan=self._plan)
+        else:
+            z = torch.stack(self.channel_outputs(), dim=1)             # [rows_per_rank, P, repr]
+            att = model.att if model.channel_aggr == 'att' else None
+            fused_local = F_.fuse_channels(z, att, model.channel_aggr, metapath_idx)
         fused_rm = all_gather_rows(fused_local, self.group)            # [padded, repr], rank-major
         return fused_rm.index_select(0, self.rm_of_global)             # node-id order, as the API promises
+
+
+class ShardedGcnPlan(object):
+    """engine.GcnPlan for row shards: same column layout, the two aggregation phases run on the
+    owned rows with ONE all-gather (forward) / reduce-scatter (backward) of the [rows, P*repr] table."""
+
+    def __init__(self, model, sp):
+        self.sp = sp
+        eil = model.meta_path_edge_index_list
+        self.P = len(model.pea_channels)
+        self.first_rels, self.rel_of_path, seen = [], [], {}
+        for p in range(self.P):
+            rel = sp.relation(eil[p][0])
+            if id(rel) not in seen:
+                seen[id(rel)] = len(self.first_rels)
+                self.first_rels.append(rel)
+            self.rel_of_path.append(seen[id(rel)])
+        groups, index = [], {}
+        for p in range(self.P):
+            rel = sp.relation(eil[p][1])
+            if id(rel) not in index:
+                index[id(rel)] = len(groups)
+                groups.append((rel, []))
+            groups[index[id(rel)]][1].append(p)
+        self.groups = groups
+        self.order = [p for _, members in groups for p in members]
+        self.slot = {p: s for s, p in enumerate(self.order)}
+        self.order_t = torch.tensor(self.order, dtype=torch.long, device=model.x.device)
+        first = model.pea_channels[0].gnn_layers
+        self.emb, self.hidden, self.repr = first[0].in_channels, first[0].out_channels, first[1].out_channels
+
+    def head_forward(self, x):
+        rpr = self.sp.plan.rows_per_rank
+        outs = []
+        for rel in self.first_rels:
+            out = torch.empty(rpr, x.shape[1], dtype=torch.float32, device=x.device)
+            outs.append(F_.spmm_raw(rel.fwd('orig'), x, x.shape[1], out, rel.scale_local, rel.scale_orig, False))
+        return outs
+
+    def head_backward(self, grads):
+        dx = None
+        for rel, d in zip(self.first_rels, grads):
+            if d is None:
+                continue
+            d = F_._rows(d)
+            if dx is None:
+                dx = torch.empty(self.sp.plan.num_nodes, d.shape[1], dtype=torch.float32, device=d.device)
+                F_.spmm_raw(rel.bwd('orig'), d, d.shape[1], dx, rel.scale_orig, rel.scale_local, False)
+            else:
+                F_.spmm_raw(rel.bwd('orig'), d, d.shape[1], dx, rel.scale_orig, rel.scale_local, False, accumulate=True)
+        return dx
+
+    def last_forward(self, t2, z, bias_all):
+        table = raw_all_gather(t2, self.sp.group)                      # the step's only all-gather
+        D, start = self.repr, 0
+        for rel, members in self.groups:
+            width = len(members) * D
+            F_.spmm_raw(rel.fwd('rm'), table[:, start:start + width], width, z[:, start:start + width],
+                        rel.scale_local, rel.scale_rm, False, bias_all[start:start + width])
+            start += width
+
+    def last_backward(self, dz):
+        dtab = torch.empty(self.sp.plan.padded, dz.shape[1], dtype=torch.float32, device=dz.device)
+        D, start = self.repr, 0
+        for rel, members in self.groups:
+            width = len(members) * D
+            F_.spmm_raw(rel.bwd('rm'), dz[:, start:start + width], width, dtab[:, start:start + width],
+                        rel.scale_rm, rel.scale_local, False)
+            start += width
+        return raw_reduce_scatter(dtab, self.sp.group)                 # ... and its only reduce-scatter
 
 
 def shard_model(model, world_size=None, rank=None, group=None):

@@ -52,6 +52,49 @@ class GcnPlan(object):
         first = model.pea_channels[0].gnn_layers
         self.emb, self.hidden, self.repr = first[0].in_channels, first[0].out_channels, first[1].out_channels
 
+    # ---- data movement of the two aggregation phases (overridden by the row-sharded plan) ----------
+    def rows(self, x):
+        return x.shape[0]
+
+    def head_forward(self, x):
+        outs = []
+        for g in self.first_graphs:
+            dis = g.gcn_dis
+            outs.append(F_.spmm_raw(g.fwd, x, x.shape[1], torch.empty_like(x), dis, dis, True))
+        return outs
+
+    def head_backward(self, grads):
+        dx = None
+        for g, d in zip(self.first_graphs, grads):
+            if d is None:
+                continue
+            d = F_._rows(d)
+            dis = g.gcn_dis
+            if dx is None:
+                dx = F_.spmm_raw(g.bwd, d, d.shape[1], torch.empty_like(d), dis, dis, True)
+            else:
+                F_.spmm_raw(g.bwd, d, d.shape[1], dx, dis, dis, True, accumulate=True)
+        return dx
+
+    def last_forward(self, t2, z, bias_all):
+        D, start = self.repr, 0
+        for g, members in self.groups:
+            width = len(members) * D
+            dis = g.gcn_dis
+            F_.spmm_raw(g.fwd, t2[:, start:start + width], width, z[:, start:start + width], dis, dis, True,
+                        bias_all[start:start + width])
+            start += width
+
+    def last_backward(self, dz):
+        dt2 = torch.empty_like(dz)
+        D, start = self.repr, 0
+        for g, members in self.groups:
+            width = len(members) * D
+            dis = g.gcn_dis
+            F_.spmm_raw(g.bwd, dz[:, start:start + width], width, dt2[:, start:start + width], dis, dis, True)
+            start += width
+        return dt2
+
     @staticmethod
     def applies(model):
         from .models.families import _GCNLayer
@@ -75,27 +118,12 @@ class _GcnHead(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, plan):
         x = F_._rows(F_._req(x, 'x'))
-        outs = []
-        for g in plan.first_graphs:
-            dis = g.gcn_dis
-            outs.append(F_.spmm_raw(g.fwd, x, x.shape[1], torch.empty_like(x), dis, dis, True))
         ctx.plan = plan
-        return tuple(outs)
+        return tuple(plan.head_forward(x))
 
     @staticmethod
     def backward(ctx, *grads):
-        plan = ctx.plan
-        dx = None
-        for g, d in zip(plan.first_graphs, grads):
-            if d is None:
-                continue
-            d = F_._rows(d)
-            dis = g.gcn_dis
-            if dx is None:
-                dx = F_.spmm_raw(g.bwd, d, d.shape[1], torch.empty_like(d), dis, dis, True)
-            else:
-                F_.spmm_raw(g.bwd, d, d.shape[1], dx, dis, dis, True, accumulate=True)
-        return dx, None
+        return ctx.plan.head_backward(grads), None
 
 
 class _GcnBody(torch.autograd.Function):
@@ -121,13 +149,7 @@ class _GcnBody(torch.autograd.Function):
             h1.append(h)
         z = torch.empty(n, wide, dtype=torch.float32, device=dev)
         bias_all = torch.cat([b2[p] for p in plan.order])
-        start = 0
-        for g, members in plan.groups:
-            width = len(members) * D
-            dis = g.gcn_dis
-            F_.spmm_raw(g.fwd, t2[:, start:start + width], width, z[:, start:start + width], dis, dis, True,
-                        bias_all[start:start + width])
-            start += width
+        plan.last_forward(t2, z, bias_all)
         del t2
         att_perm = att.reshape(P, D).index_select(0, plan.order_t).contiguous() if att is not None else None
         out = torch.empty(n, D, dtype=torch.float32, device=dev)
@@ -165,13 +187,7 @@ class _GcnBody(torch.autograd.Function):
                          dout.stride(0), F_._ptr(dz), wide, F_._ptr(d_att_perm), F_._ptr(ws), need, F_._stream())
         db2_all = torch.empty(wide, dtype=torch.float32, device=dev)
         F_.wgrad_raw(None, dz, 0, wide, 0, None, db2_all)                     # every metapath's d b2 at once
-        dt2 = torch.empty(n, wide, dtype=torch.float32, device=dev)
-        start = 0
-        for g, members in plan.groups:
-            width = len(members) * D
-            dis = g.gcn_dis
-            F_.spmm_raw(g.bwd, dz[:, start:start + width], width, dt2[:, start:start + width], dis, dis, True)
-            start += width
+        dt2 = plan.last_backward(dz)
         dA1 = [None] * n_rel
         grads = []
         dp1 = torch.empty(n, H, dtype=torch.float32, device=dev)
@@ -199,11 +215,13 @@ class _GcnBody(torch.autograd.Function):
         return (None, d_att, None, None, None) + tuple(dA1) + tuple(grads)
 
 
-def gcn_forward(model, metapath_idx=None):
-    """model.forward() through the fused engine (same result as the per-layer path)."""
-    plan = getattr(model, '_gcn_plan', None)
+def gcn_forward(model, metapath_idx=None, plan=None):
+    """model.forward() through the fused engine (same result as the per-layer path).  With a
+    row-sharded ``plan`` (distributed.ShardedGcnPlan) the result is this rank's rows."""
     if plan is None:
-        plan = model._gcn_plan = GcnPlan(model)
+        plan = getattr(model, '_gcn_plan', None)
+        if plan is None:
+            plan = model._gcn_plan = GcnPlan(model)
     a1 = _GcnHead.apply(model.x, plan)
     params = []
     for ch in model.pea_channels:

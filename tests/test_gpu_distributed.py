@@ -33,7 +33,8 @@ def _worker(rank, world, port, kind, entity_aware, ret):
         torch.cuda.set_device(0)
         ds = SyntheticHIN('tiny', seed=7, entity_aware=entity_aware)
         torch.manual_seed(2020)
-        model = product_model_for(ds, kind, entity_aware=entity_aware)
+        model = product_model_for(ds, kind.split('-')[0], entity_aware=entity_aware)
+        model.fused_engine = not kind.endswith('-layers')       # engine.py plan vs per-layer modules
         import random, numpy as np
         random.seed(1); np.random.seed(1); torch.manual_seed(1)
         ds.cf_negative_sampling()
@@ -78,7 +79,7 @@ def _worker(rank, world, port, kind, entity_aware, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('kind,entity_aware', [('gcn', False), ('sage', True), ('gat', False)])
+@pytest.mark.parametrize('kind,entity_aware', [('gcn', False), ('gcn-layers', True), ('sage', True), ('gat', False)])
 @pytest.mark.parametrize('world', [2, 3])
 def test_sharded_model_matches_unsharded(kind, entity_aware, world):
     mgr = mp.Manager()
