@@ -210,6 +210,9 @@ def run_product(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # collectives run on NCCL's own stream; with record_stream bookkeeping the caching allocator
+        # cannot reuse their buffers until a host sync, and an un-synced step loop keeps growing
+        os.environ.setdefault('TORCH_NCCL_AVOID_RECORD_STREAMS', '1')
         dist.init_process_group('nccl', device_id=dev)
 
     ds = SyntheticHIN(args.workload, seed=1234)
