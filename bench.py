@@ -58,10 +58,12 @@ class ClockSampler(object):
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, gpu_index):
-        self.gpu, self.lines, self.proc = gpu_index, [], None
+    def __init__(self, gpu_index, enabled=True):
+        self.gpu, self.lines, self.proc, self.enabled = gpu_index, [], None, enabled
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '200'],
@@ -272,7 +274,7 @@ def run_product(args):
     F_.PROFILE = []                 # CUDA events around the aggregation launches only (the roofline kernel)
     launches0 = _lib.load().peagnn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local, enabled=(rank == 0 and not os.environ.get('PEAGNN_BENCH_NO_CLOCKS'))) as clocks:
         barrier()
         e0.record()
         for k in range(K):

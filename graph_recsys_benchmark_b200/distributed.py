@@ -238,12 +238,15 @@ def shard_gat_aggregate(H, ai, aj, rel, heads, bias=None, relu=False):
     return _ShardGatAggregate.apply(H, ai, aj, bias, rel, heads, relu)
 
 
-def raw_all_gather(local, group=None):
+def raw_all_gather(local, group=None, out=None):
     """[rows_per_rank, F] -> [R * rows_per_rank, F] (rank-major).  NCCL all_gather_into_tensor; gloo
-    (CPU / single-GPU test rigs) goes through the list form."""
+    (CPU / single-GPU test rigs) goes through the list form.  ``out`` lets the caller keep one
+    persistent receive buffer (buffers that cross to NCCL's stream are slow to return to the
+    caching allocator; re-allocating 100s of MB per step ends in cudaMalloc / cudaFree stalls)."""
     local = local.contiguous()
     world = dist.get_world_size(group)
-    out = torch.empty(world * local.shape[0], local.shape[1], dtype=local.dtype, device=local.device)
+    if out is None:
+        out = torch.empty(world * local.shape[0], local.shape[1], dtype=local.dtype, device=local.device)
     if dist.get_backend(group) == 'gloo':
         dist.all_gather(list(out.chunk(world, dim=0)), local, group=group)
     else:
@@ -251,7 +254,7 @@ def raw_all_gather(local, group=None):
     return out
 
 
-def raw_reduce_scatter(full, group=None):
+def raw_reduce_scatter(full, group=None, out=None):
     """Sum over ranks of [R * rows_per_rank, F], each rank keeping its own row block."""
     full = full.contiguous()
     world = dist.get_world_size(group)
@@ -261,7 +264,7 @@ def raw_reduce_scatter(full, group=None):
         dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
         r = dist.get_rank(group)
         return full[r * rows:(r + 1) * rows].contiguous()
-    local = torch.empty(rows, full.shape[1], dtype=full.dtype, device=full.device)
+    local = out if out is not None else torch.empty(rows, full.shape[1], dtype=full.dtype, device=full.device)
     dist.reduce_scatter_tensor(local, full, op=dist.ReduceOp.SUM, group=group)
     return local
 
@@ -285,13 +288,25 @@ def all_gather_rows(local, group=None):
     return _AllGatherRows.apply(local, group)
 
 
+_flat_buffers = {}
+
+
 def allreduce_gradients(params, group=None):
     """Sum the parameter gradients over ranks with one flat all-reduce (data-parallel BPR batches +
     row-sharded propagation both leave per-rank partial sums)."""
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    total = sum(g.numel() for g in grads)
+    key = (total, grads[0].device, grads[0].dtype)
+    flat = _flat_buffers.get(key)
+    if flat is None:                                   # one persistent bucket per model (see raw_all_gather)
+        flat = _flat_buffers[key] = torch.empty(total, dtype=grads[0].dtype, device=grads[0].device)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        flat[off:off + n].copy_(g.reshape(-1))
+        off += n
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     off = 0
     for g in grads:
@@ -513,6 +528,7 @@ class ShardedGcnPlan(object):
         self.order_t = torch.tensor(self.order, dtype=torch.long, device=model.x.device)
         first = model.pea_channels[0].gnn_layers
         self.emb, self.hidden, self.repr = first[0].in_channels, first[0].out_channels, first[1].out_channels
+        self._table = self._dtab = None
 
     def head_forward(self, x):
         rpr = self.sp.plan.rows_per_rank
@@ -536,7 +552,9 @@ class ShardedGcnPlan(object):
         return dx
 
     def last_forward(self, t2, z, bias_all):
-        table = raw_all_gather(t2, self.sp.group)                      # the step's only all-gather
+        if self._table is None or self._table.shape != (self.sp.plan.padded, t2.shape[1]):
+            self._table = torch.empty(self.sp.plan.padded, t2.shape[1], dtype=torch.float32, device=t2.device)
+        table = raw_all_gather(t2, self.sp.group, out=self._table)     # the step's only all-gather
         D, start = self.repr, 0
         for rel, members in self.groups:
             width = len(members) * D
@@ -545,7 +563,9 @@ class ShardedGcnPlan(object):
             start += width
 
     def last_backward(self, dz):
-        dtab = torch.empty(self.sp.plan.padded, dz.shape[1], dtype=torch.float32, device=dz.device)
+        if self._dtab is None or self._dtab.shape != (self.sp.plan.padded, dz.shape[1]):
+            self._dtab = torch.empty(self.sp.plan.padded, dz.shape[1], dtype=torch.float32, device=dz.device)
+        dtab = self._dtab
         D, start = self.repr, 0
         for rel, members in self.groups:
             width = len(members) * D
