@@ -276,10 +276,12 @@ def run_product(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local, enabled=(rank == 0 and not os.environ.get('PEAGNN_BENCH_NO_CLOCKS'))) as clocks:
         barrier()
+        t_host = time.perf_counter()
         e0.record()
         for k in range(K):
             step(dev_batches[W + k])
         e1.record()
+        host_ms = (time.perf_counter() - t_host) * 1e3 / K       # time the host needs to ENQUEUE a step
         barrier()
     launches = int(_lib.load().peagnn_launch_count() - launches0)
     ms_total = e0.elapsed_time(e1)
@@ -354,7 +356,7 @@ def run_product(args):
                                          'dp%d (replicated propagation, NCCL all-reduce of gradients)' % world))),
             'e2e': {'value': world * B * K / (ms_e2e * 1e-3), 'unit': 'triples/s', 'h2d_bytes_per_step': B * 3 * 8,
                     'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / K, 'last_loss': last},
-            'gpu_launches': launches,
+            'gpu_launches': launches, 'host_enqueue_ms_per_step': host_ms,
             'roofline': {'bound': 'hbm', 'kernel': agg_name + ' (csr_rows_kernel / csr_chunk_kernel)',
                          'achieved': achieved, 'peak': hbm_peak, 'peak_source': peak_src, 'unit': 'GB/s',
                          'frac': (achieved / hbm_peak) if achieved else None,

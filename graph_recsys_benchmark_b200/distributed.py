@@ -302,17 +302,14 @@ def allreduce_gradients(params, group=None):
     flat = _flat_buffers.get(key)
     if flat is None:                                   # one persistent bucket per model (see raw_all_gather)
         flat = _flat_buffers[key] = torch.empty(total, dtype=grads[0].dtype, device=grads[0].device)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        flat[off:off + n].copy_(g.reshape(-1))
-        off += n
+    torch.cat([g.reshape(-1) for g in grads], out=flat)            # one launch in ...
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    off = 0
+    views, off = [], 0
     for g in grads:
         n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
+        views.append(flat[off:off + n].view_as(g))
         off += n
+    torch._foreach_copy_(grads, views)                             # ... and one multi-tensor launch out
 
 
 class ShardedPropagation(object):
