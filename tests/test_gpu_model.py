@@ -194,3 +194,39 @@ def test_engine_declines_other_shapes():
     assert not GcnPlan.applies(m)
     m.eval()                                             # ... and the per-layer path serves it
     assert m.cached_repr.shape == (ds.num_nodes, 16) and bool(torch.isfinite(m.cached_repr).all())
+
+
+@pytest.mark.parametrize('kind', ['gcn', 'gat', 'sage'])
+def test_product_matches_frozen_golden_vectors(kind):
+    """The committed golden vectors (tests/golden/oracle_vectors.pt, frozen oracle outputs on the
+    seeded tiny HIN): same triples, loss / representation / gradient within 1e-5 / 1e-4, same ranks."""
+    import os
+    frozen = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'oracle_vectors.pt'),
+                        weights_only=False)
+    g = frozen[kind]
+    ds = _dataset(entity_aware=g['entity_aware'])
+    torch.manual_seed(2020)
+    oracle = oracle_model_for(ds, kind, entity_aware=g['entity_aware'])       # same init draw as the script
+    model = product_model_for(ds, kind, entity_aware=g['entity_aware'])
+    model.load_state_dict(oracle.state_dict())
+    osolver.seed_everything(1)
+    ds.cf_negative_sampling()
+    batch = ds.get_batch(list(range(128)))
+    assert torch.equal(batch, g['batch'])                                       # integer: bit-exact
+    model.train()
+    loss = model.loss(batch.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - g['loss']) <= 1e-5 * abs(g['loss'])
+    assert rel_err(model.cached_repr[:8], g['repr_rows']) < 1e-5
+    assert abs(float(model.cached_repr.double().sum()) - g['repr_sum']) <= 1e-4 * abs(g['repr_sum']) + 1e-4
+    assert rel_err(model.x.grad[:4], g['x_grad_rows']) < 1e-4
+    from graph_recsys_benchmark_b200.solvers import BaseSolver
+    solver = BaseSolver(None, {}, {}, {'device': DEV, 'num_neg_candidates': 99, 'batch_size': 128})
+    model.eval()
+    np.random.seed(99)
+    (hr, nd, auc, el), per = solver.metrics(1, 1, model, ds, return_per_user=True)
+    ranks = per[:, 34].long().cpu()
+    assert float((ranks == g['ranks']).float().mean()) >= 0.975
+    if torch.equal(ranks, g['ranks']):
+        assert hr[5] == g['hr10'] and abs(nd[5] - g['ndcg10']) < 1e-12
+    assert abs(auc[0] - g['auc']) < 2e-3 and abs(el[0] - g['eval_loss']) <= 1e-4 * abs(g['eval_loss'])

@@ -79,3 +79,26 @@ def test_csr_by_key_is_stable_and_drops_self_loops():
     assert rowptr.tolist() == [0, 0, 1, 1, 4, 6, 6]
     assert col.tolist() == [4, 0, 0, 1, 2, 0]
     assert eid.tolist() == [5, 0, 1, 2, 4, 6]
+
+
+def test_oracle_reproduces_frozen_vectors():
+    """tests/golden/oracle_vectors.pt was written by tests/golden/make_oracle_vectors.py; the oracle
+    (and the seeded host logic feeding it) must keep producing exactly those numbers."""
+    import os, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, 'golden'))
+    import make_oracle_vectors
+    frozen = torch.load(os.path.join(here, 'golden', 'oracle_vectors.pt'), weights_only=False)
+    fresh = make_oracle_vectors.build()
+    assert set(frozen) == set(fresh)
+    for kind in ('gcn', 'gat', 'sage'):
+        a, b = frozen[kind], fresh[kind]
+        assert torch.equal(a['batch'], b['batch']) and torch.equal(a['ranks'], b['ranks'])
+        assert abs(a['loss'] - b['loss']) <= 1e-6 * abs(a['loss'])
+        assert torch.allclose(a['repr_rows'], b['repr_rows'], rtol=1e-5, atol=1e-7)
+        assert torch.allclose(a['x_grad_rows'], b['x_grad_rows'], rtol=1e-4, atol=1e-8)
+        assert a['hr10'] == b['hr10'] and abs(a['ndcg10'] - b['ndcg10']) < 1e-12
+    for k in ('rowptr', 'col', 'eid'):
+        assert torch.equal(frozen['csr_user2item_by_target'][k], fresh['csr_user2item_by_target'][k])
+    assert torch.equal(frozen['train_triples_first_64'], fresh['train_triples_first_64'])
+    assert torch.equal(frozen['candidates_user0'], fresh['candidates_user0'])
