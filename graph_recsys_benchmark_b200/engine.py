@@ -24,23 +24,26 @@ from .graph import get_graph
 
 
 class GcnPlan(object):
-    """Static schedule of a model: which relation feeds which metapath, and the column layout."""
+    """Static schedule of a model: which relation feeds which metapath, and the column layout.
+    ``kind`` 'gcn' (normalised sum with self loops) or 'sage' (mean over in-edges, no self loops)."""
 
-    def __init__(self, model):
+    def __init__(self, model, kind='gcn'):
         n = model.x.shape[0]
+        self.kind = kind
         eil = model.meta_path_edge_index_list
         self.P = len(model.pea_channels)
         self.first_graphs, self.rel_of_path = [], []
         seen = {}
+        keep = kind == 'sage'
         for p in range(self.P):
-            g = get_graph(eil[p][0], n)
+            g = get_graph(eil[p][0], n, keep_self_loops=keep)
             if id(g) not in seen:
                 seen[id(g)] = len(self.first_graphs)
                 self.first_graphs.append(g)
             self.rel_of_path.append(seen[id(g)])
         groups, index = [], {}
         for p in range(self.P):
-            g = get_graph(eil[p][1], n)
+            g = get_graph(eil[p][1], n, keep_self_loops=keep)
             if id(g) not in index:
                 index[id(g)] = len(groups)
                 groups.append((g, []))
@@ -53,14 +56,17 @@ class GcnPlan(object):
         self.emb, self.hidden, self.repr = first[0].in_channels, first[0].out_channels, first[1].out_channels
 
     # ---- data movement of the two aggregation phases (overridden by the row-sharded plan) ----------
-    def rows(self, x):
-        return x.shape[0]
+    def _scales(self, g, transposed):
+        """(row scale, column scale, implicit self loop) of the aggregation operator or its transpose."""
+        if self.kind == 'gcn':
+            return g.gcn_dis, g.gcn_dis, True
+        return (None, g.inv_in_degree, False) if transposed else (g.inv_in_degree, None, False)
 
     def head_forward(self, x):
         outs = []
         for g in self.first_graphs:
-            dis = g.gcn_dis
-            outs.append(F_.spmm_raw(g.fwd, x, x.shape[1], torch.empty_like(x), dis, dis, True))
+            rs, cs, loop = self._scales(g, False)
+            outs.append(F_.spmm_raw(g.fwd, x, x.shape[1], torch.empty_like(x), rs, cs, loop))
         return outs
 
     def head_backward(self, grads):
@@ -69,19 +75,19 @@ class GcnPlan(object):
             if d is None:
                 continue
             d = F_._rows(d)
-            dis = g.gcn_dis
+            rs, cs, loop = self._scales(g, True)
             if dx is None:
-                dx = F_.spmm_raw(g.bwd, d, d.shape[1], torch.empty_like(d), dis, dis, True)
+                dx = F_.spmm_raw(g.bwd, d, d.shape[1], torch.empty_like(d), rs, cs, loop)
             else:
-                F_.spmm_raw(g.bwd, d, d.shape[1], dx, dis, dis, True, accumulate=True)
+                F_.spmm_raw(g.bwd, d, d.shape[1], dx, rs, cs, loop, accumulate=True)
         return dx
 
     def last_forward(self, t2, z, bias_all):
         D, start = self.repr, 0
         for g, members in self.groups:
             width = len(members) * D
-            dis = g.gcn_dis
-            F_.spmm_raw(g.fwd, t2[:, start:start + width], width, z[:, start:start + width], dis, dis, True,
+            rs, cs, loop = self._scales(g, False)
+            F_.spmm_raw(g.fwd, t2[:, start:start + width], width, z[:, start:start + width], rs, cs, loop,
                         bias_all[start:start + width])
             start += width
 
@@ -90,19 +96,20 @@ class GcnPlan(object):
         D, start = self.repr, 0
         for g, members in self.groups:
             width = len(members) * D
-            dis = g.gcn_dis
-            F_.spmm_raw(g.bwd, dz[:, start:start + width], width, dt2[:, start:start + width], dis, dis, True)
+            rs, cs, loop = self._scales(g, True)
+            F_.spmm_raw(g.bwd, dz[:, start:start + width], width, dt2[:, start:start + width], rs, cs, loop)
             start += width
         return dt2
 
     @staticmethod
-    def applies(model):
-        from .models.families import _GCNLayer
+    def applies(model, kind='gcn'):
+        from .models.families import _GCNLayer, _SageLayer
+        layer_class = _GCNLayer if kind == 'gcn' else _SageLayer
         if getattr(model, 'channel_aggr', None) not in ('att', 'mean'):
             return False
         dims = None
         for ch in model.pea_channels:
-            if ch.num_steps != 2 or not all(isinstance(l, _GCNLayer) for l in ch.gnn_layers):
+            if ch.num_steps != 2 or not all(isinstance(l, layer_class) for l in ch.gnn_layers):
                 return False
             d = (ch.gnn_layers[0].in_channels, ch.gnn_layers[0].out_channels, ch.gnn_layers[1].in_channels,
                  ch.gnn_layers[1].out_channels)
@@ -231,3 +238,121 @@ def gcn_forward(model, metapath_idx=None, plan=None):
     mode = 0 if model.channel_aggr == 'att' else 1
     skip = -1 if metapath_idx is None else int(metapath_idx)
     return _GcnBody.apply(plan, att, mode, skip, len(a1), *a1, *params)
+
+
+class _SageBody(torch.autograd.Function):
+    """PEASage counterpart of _GcnBody.  Per metapath p (nn.Linear weights are [out, in]):
+         H1 = relu(M1_r Wrel1^T + brel1 + x Wroot1^T);   T2 = H1 Wrel2^T  -> its column slot;
+         Z  = mean_agg(T2) + brel2  (one launch per last-step relation)  + H1 Wroot2^T (accumulated)."""
+
+    @staticmethod
+    def forward(ctx, plan, att, mode, skip, n_rel, x, *tensors):
+        x = F_._rows(x)
+        M1 = [F_._rows(t) for t in tensors[:n_rel]]
+        params = [t.contiguous() for t in tensors[n_rel:]]
+        P, D, H = plan.P, plan.repr, plan.hidden
+        par = [params[6 * p:6 * p + 6] for p in range(P)]      # Wrel1, brel1, Wroot1, Wrel2, brel2, Wroot2
+        dev, n, wide = x.device, x.shape[0], P * D
+        t2 = torch.empty(n, wide, dtype=torch.float32, device=dev)
+        h1 = []
+        for p in range(P):
+            wrel1, brel1, wroot1, wrel2, _, _ = par[p]
+            h = torch.empty(n, H, dtype=torch.float32, device=dev)
+            F_.linear_raw(M1[plan.rel_of_path[p]], wrel1, h, True, brel1)
+            F_.linear_raw(x, wroot1, h, True, None, True, True)                    # += root term, then relu
+            s = plan.slot[p]
+            F_.linear_raw(h, wrel2, t2[:, s * D:(s + 1) * D], True)
+            h1.append(h)
+        z = torch.empty(n, wide, dtype=torch.float32, device=dev)
+        plan.last_forward(t2, z, torch.cat([par[p][4] for p in plan.order]))
+        del t2
+        for p in range(P):
+            s = plan.slot[p]
+            F_.linear_raw(h1[p], par[p][5], z[:, s * D:(s + 1) * D], True, None, False, True)   # += H1 Wroot2^T
+        att_perm = att.reshape(P, D).index_select(0, plan.order_t).contiguous() if att is not None else None
+        out = torch.empty(n, D, dtype=torch.float32, device=dev)
+        skip_slot = plan.slot[skip] if skip >= 0 else -1
+        with F_._on(dev):
+            F_._lib.call('peagnn_fuse_forward', F_._ptr(z), wide, n, P, D, F_._ptr(att_perm), mode, skip_slot,
+                         F_._ptr(out), D, F_._stream())
+        ctx.plan, ctx.mode, ctx.skip, ctx.n_rel = plan, mode, skip, n_rel
+        ctx.att_shape = att.shape if att is not None else None
+        ctx.save_for_backward(z, att_perm, x, *M1, *h1, *[w for p in range(P) for w in (par[p][0], par[p][2], par[p][3], par[p][5])])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        plan, n_rel = ctx.plan, ctx.n_rel
+        if ctx.skip >= 0:
+            raise RuntimeError('metapath ablation (metapath_idx) is an evaluation-only path (models/base.py:88-96)')
+        P, D, H, E = plan.P, plan.repr, plan.hidden, plan.emb
+        saved = ctx.saved_tensors
+        z, att_perm, x = saved[0], saved[1], saved[2]
+        M1 = saved[3:3 + n_rel]
+        h1 = saved[3 + n_rel:3 + n_rel + P]
+        ws = saved[3 + n_rel + P:]
+        dev, n, wide = z.device, z.shape[0], P * D
+        dout = F_._rows(dout)
+        dz = torch.empty(n, wide, dtype=torch.float32, device=dev)
+        d_att_perm = torch.empty(P, D, dtype=torch.float32, device=dev) if ctx.mode == 0 else None
+        need = int(F_._lib.query('peagnn_fuse_workspace_floats', n, P, D)) if ctx.mode == 0 else 0
+        wsp = F_._ws(need, dev) if ctx.mode == 0 else None
+        with F_._on(dev):
+            F_._lib.call('peagnn_fuse_backward', F_._ptr(z), wide, n, P, D, F_._ptr(att_perm), ctx.mode, F_._ptr(dout),
+                         dout.stride(0), F_._ptr(dz), wide, F_._ptr(d_att_perm), F_._ptr(wsp), need, F_._stream())
+        db2_all = torch.empty(wide, dtype=torch.float32, device=dev)
+        F_.wgrad_raw(None, dz, 0, wide, 0, None, db2_all)
+        dt2 = plan.last_backward(dz)
+        dM1 = [None] * n_rel
+        dx = None
+        grads = []
+        dp1 = torch.empty(n, H, dtype=torch.float32, device=dev)
+        for p in range(P):
+            wrel1, wroot1, wrel2, wroot2 = ws[4 * p:4 * p + 4]
+            s = plan.slot[p]
+            d_z, d_t2 = dz[:, s * D:(s + 1) * D], dt2[:, s * D:(s + 1) * D]
+            dwroot2 = torch.empty_like(wroot2)
+            F_.wgrad_raw(h1[p], d_z, H, D, True, dwroot2, None)
+            dwrel2 = torch.empty_like(wrel2)
+            F_.wgrad_raw(h1[p], d_t2, H, D, True, dwrel2, None)
+            F_.linear_raw(d_z, wroot2, dp1, False)                                   # dH1 = dZ Wroot2 ...
+            F_.linear_raw(d_t2, wrel2, dp1, False, None, False, True, out_mask=h1[p])  # ... + dT2 Wrel2, relu-gated
+            r = plan.rel_of_path[p]
+            dwrel1, dbrel1 = torch.empty_like(wrel1), torch.empty(H, dtype=torch.float32, device=dev)
+            F_.wgrad_raw(M1[r], dp1, E, H, True, dwrel1, dbrel1)
+            dwroot1 = torch.empty_like(wroot1)
+            F_.wgrad_raw(x, dp1, E, H, True, dwroot1, None)
+            if dM1[r] is None:
+                dM1[r] = torch.empty(n, E, dtype=torch.float32, device=dev)
+                F_.linear_raw(dp1, wrel1, dM1[r], False)
+            else:
+                F_.linear_raw(dp1, wrel1, dM1[r], False, accumulate=True)
+            if dx is None:
+                dx = torch.empty(n, E, dtype=torch.float32, device=dev)
+                F_.linear_raw(dp1, wroot1, dx, False)
+            else:
+                F_.linear_raw(dp1, wroot1, dx, False, accumulate=True)
+            grads.extend([dwrel1, dbrel1, dwroot1, dwrel2, db2_all[s * D:(s + 1) * D], dwroot2])
+        d_att = None
+        if d_att_perm is not None:
+            d_att = torch.empty_like(d_att_perm)
+            d_att.index_copy_(0, plan.order_t, d_att_perm)
+            d_att = d_att.reshape(ctx.att_shape)
+        return (None, d_att, None, None, None, dx) + tuple(dM1) + tuple(grads)
+
+
+def sage_forward(model, metapath_idx=None):
+    """model.forward() of a standard PEASage model through the fused engine."""
+    plan = getattr(model, '_sage_plan', None)
+    if plan is None:
+        plan = model._sage_plan = GcnPlan(model, 'sage')
+    m1 = _GcnHead.apply(model.x, plan)
+    params = []
+    for ch in model.pea_channels:
+        l0, l1 = ch.gnn_layers
+        params.extend([l0.lin_rel.weight, l0.lin_rel.bias, l0.lin_root.weight,
+                       l1.lin_rel.weight, l1.lin_rel.bias, l1.lin_root.weight])
+    att = model.att if model.channel_aggr == 'att' else None
+    mode = 0 if model.channel_aggr == 'att' else 1
+    skip = -1 if metapath_idx is None else int(metapath_idx)
+    return _SageBody.apply(plan, att, mode, skip, len(m1), model.x, *m1, *params)

@@ -168,10 +168,11 @@ class PEABaseRecsysModel(GraphRecsysModel):
             ok = getattr(self, '_engine_ok', None)
             if ok is None:
                 from ..engine import GcnPlan
-                ok = self._engine_ok = GcnPlan.applies(self)
+                ok = self._engine_ok = ('gcn' if GcnPlan.applies(self, 'gcn') else
+                                        'sage' if GcnPlan.applies(self, 'sage') else '')
             if ok:
-                from ..engine import gcn_forward
-                return gcn_forward(self, metapath_idx)
+                from .. import engine
+                return (engine.gcn_forward if ok == 'gcn' else engine.sage_forward)(self, metapath_idx)
         z = torch.stack(self.channel_outputs(), dim=1)                  # [N, P, repr]
         att = self.att if self.channel_aggr == 'att' else None
         return F_.fuse_channels(z, att, self.channel_aggr, metapath_idx)

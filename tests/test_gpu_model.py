@@ -151,17 +151,18 @@ def test_experiment_cli_trains_evaluates_checkpoints_and_resumes(tmp_path, monke
     assert "Loaded checkpoint_backup" in out and 'Run: 1, epoch: 3, HR@5' in out and 'Run: 1, epoch: 2, HR@5' not in out
 
 
+@pytest.mark.parametrize('kind', ['gcn', 'sage'])
 @pytest.mark.parametrize('aggr', ['att', 'mean'])
 @pytest.mark.parametrize('entity_aware', [False, True])
-def test_fused_engine_equals_layer_path(aggr, entity_aware):
+def test_fused_engine_equals_layer_path(kind, aggr, entity_aware):
     """engine.py (two autograd nodes, planned buffers) and the per-layer modules run the same
     kernels: loss, representation and every gradient agree to rounding."""
     from graph_recsys_benchmark_b200.engine import GcnPlan
     ds = _dataset()
     batch = _batch(ds, 300, entity_aware).to(DEV)
     torch.manual_seed(11)
-    model = product_model_for(ds, 'gcn', entity_aware=entity_aware, channel_aggr=aggr)
-    assert GcnPlan.applies(model)
+    model = product_model_for(ds, kind, entity_aware=entity_aware, channel_aggr=aggr)
+    assert GcnPlan.applies(model, kind)
     model.train()
     res = {}
     for fused in (True, False):
@@ -188,8 +189,9 @@ def test_fused_engine_equals_layer_path(aggr, entity_aware):
 def test_engine_declines_other_shapes():
     from graph_recsys_benchmark_b200.engine import GcnPlan
     ds = _dataset()
-    assert not GcnPlan.applies(product_model_for(ds, 'sage'))
-    assert not GcnPlan.applies(product_model_for(ds, 'gat'))
+    assert not GcnPlan.applies(product_model_for(ds, 'sage'), 'gcn')
+    assert not GcnPlan.applies(product_model_for(ds, 'gcn'), 'sage')
+    assert not GcnPlan.applies(product_model_for(ds, 'gat'), 'gcn') and not GcnPlan.applies(product_model_for(ds, 'gat'), 'sage')
     m = product_model_for(ds, 'gcn', hidden=16)          # hidden == repr: both steps aggregate first
     assert not GcnPlan.applies(m)
     m.eval()                                             # ... and the per-layer path serves it
