@@ -243,3 +243,62 @@ def test_eval_rank_matches_reference_metrics(U, C, n_pos):
         pair = -(s[k, :n_pos].double().view(-1, 1) - s[k, n_pos:].double().view(1, -1)).sigmoid().log().sum()
         assert abs(pu[k, 33] - pair.item()) <= 1e-5 * abs(pair.item())
     assert np.allclose(means.cpu().numpy(), pu.mean(axis=0), rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize('feat', [4, 8, 12, 32, 100, 112, 128, 144, 208, 256, 320])
+@pytest.mark.parametrize('mode', ['gcn', 'mean'])
+def test_aggregation_every_width_class(feat, mode):
+    """Slot geometries G = 4 / 8 / 16 / 32 and 1, 2, 4 float4 chunks per lane, light + heavy rows,
+    against an independent torch index_add reduction (fp64)."""
+    from graph_recsys_benchmark_b200 import functional as F_, graph as pgraph
+    n = 700
+    ei = random_edge_index(n, 9000, 21, multi=400, dst_range=(0, 90))            # 90 busy rows, 610 empty
+    old = pgraph.HEAVY_THRESHOLD, pgraph.CHUNK_EDGES
+    pgraph.HEAVY_THRESHOLD, pgraph.CHUNK_EDGES = 48, 64
+    try:
+        g = _graph(ei, n)
+        assert g.fwd.n_heavy > 0 and g.fwd.n_chunks > g.fwd.n_heavy
+        x = torch.randn(n, feat)
+        xd = x.double()
+        src, dst = ei[0], ei[1]
+        nl = src != dst
+        if mode == 'gcn':
+            dis = (torch.bincount(src[nl], minlength=n).double() + 1).pow(-0.5)
+            ref = torch.zeros(n, feat, dtype=torch.float64).index_add_(0, dst[nl], xd[src[nl]] * (dis[src[nl]] * dis[dst[nl]]).view(-1, 1))
+            ref += xd * (dis * dis).view(-1, 1)
+            got = F_.spmm_raw(g.fwd, x.to(DEV), feat, torch.empty(n, feat, device=DEV), g.gcn_dis, g.gcn_dis, True)
+        else:
+            cnt = torch.bincount(dst[nl], minlength=n).double().clamp(min=1)
+            ref = torch.zeros(n, feat, dtype=torch.float64).index_add_(0, dst[nl], xd[src[nl]]) / cnt.view(-1, 1)
+            got = F_.spmm_raw(g.fwd, x.to(DEV), feat, torch.empty(n, feat, device=DEV), g.inv_in_degree, None, False)
+        assert rel_err(got, ref) < TOL
+    finally:
+        pgraph.HEAVY_THRESHOLD, pgraph.CHUNK_EDGES = old
+        pgraph.clear_cache()
+
+
+@pytest.mark.parametrize('D', [8, 32])
+def test_scoring_kernels_other_repr_dims(D):
+    from graph_recsys_benchmark_b200 import functional as F_
+    n, B = 300, 257
+    fc1, fc2 = _fc(D)
+    r = torch.randn(n, D)
+    batch = torch.randint(0, n, (B, 3))
+    f1, f2 = torch.nn.Linear(2 * D, D).double(), torch.nn.Linear(D, 1).double()
+    f1.load_state_dict(fc1.state_dict()); f2.load_state_dict(fc2.state_dict())
+    ro = r.clone().double().requires_grad_(True)
+
+    def pred(u, i):
+        return f2(torch.relu(f1(torch.cat([ro[u], ro[i]], dim=-1))))
+    lo = -(pred(batch[:, 0], batch[:, 1]) - pred(batch[:, 0], batch[:, 2])).sigmoid().log().sum()
+    lo.backward()
+    rp = r.clone().to(DEV).requires_grad_(True)
+    ps = [t.detach().clone().to(DEV).requires_grad_(True) for t in (fc1.weight, fc1.bias, fc2.weight, fc2.bias)]
+    lp = F_.bpr_loss(rp, ps[0], ps[1], ps[2], ps[3], batch.to(DEV))
+    lp.backward()
+    assert abs(lp.item() - lo.item()) / abs(lo.item()) < TOL and rel_err(rp.grad, ro.grad) < 10 * TOL
+    assert rel_err(ps[0].grad, f1.weight.grad) < 10 * TOL and rel_err(ps[2].grad, f2.weight.grad) < 10 * TOL
+    users, cand = torch.randint(0, n, (40,)), torch.randint(0, n, (40, 50))
+    _, _, scores = F_.eval_rank(r.to(DEV), users.to(DEV), cand.to(DEV), 1, *[p.detach() for p in ps], return_scores=True)
+    ref = f2(torch.relu(f1(torch.cat([r.double()[users].unsqueeze(1).expand(-1, 50, -1), r.double()[cand]], dim=-1)))).squeeze(-1)
+    assert rel_err(scores, ref) < TOL
