@@ -161,10 +161,19 @@ def load_global_logger(global_logger_filepath):
 
 def load_dataset(dataset_args):
     """The reference builds MovieLens / Yelp from raw downloads (out of scope).  Here a dataset is
-    either handed over ready-made (``dataset_args['dataset_object']``) or synthesised with the
+    either handed over ready-made (``dataset_args['dataset_object']``), loaded from a processed
+    pickle in the reference's schema (``dataset_args['processed_pickle']``) or synthesised with the
     reference's schema (``dataset_args['synthetic']`` = a ``datasets.synthetic`` shape name)."""
     if dataset_args.get('dataset_object') is not None:
         return dataset_args['dataset_object']
+    if dataset_args.get('processed_pickle'):             # a reference-schema dataset_property_dict blob
+        from ..datasets import ProcessedHIN
+        return ProcessedHIN(dataset_args['processed_pickle'], dataset=dataset_args['dataset'],
+                            name=dataset_args.get('name'),
+                            num_negative_samples=dataset_args.get('num_negative_samples', 4),
+                            sampling_strategy=dataset_args.get('sampling_strategy', 'random'),
+                            entity_aware=dataset_args.get('entity_aware', False),
+                            cf_loss_type=dataset_args.get('cf_loss_type', 'BPR'))
     from ..datasets import make_synthetic_dataset
     return make_synthetic_dataset(dataset_args)
 

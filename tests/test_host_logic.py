@@ -220,3 +220,25 @@ def test_shipped_checkpoints_load_through_load_model():
         assert epoch == 30 and rec[0].shape == (30, 16) and not torch.equal(before, model.x.detach())
         assert len(opt.state) == len(list(model.parameters()))
         assert int(next(iter(opt.state.values()))['step']) == 9270
+
+
+def test_reference_schema_pickle_round_trip(tmp_path):
+    """datasets/hin_pickle.py: dump a dataset in the reference's dataset_property_dict schema, load it
+    back, and get the same graph, the same sampled triples and the same entity-aware batches."""
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN, ProcessedHIN, dump_reference_pickle
+    from graph_recsys_benchmark_b200.utils import load_dataset, update_pea_graph_input
+    src = SyntheticHIN('tiny', seed=7, entity_aware=True, sampling_strategy='unseen')
+    path = dump_reference_pickle(src, str(tmp_path / 'ml_latest-small_core_10_type_hete.pkl'))
+    ds = load_dataset({'dataset': 'Movielens', 'name': 'latest-small', 'processed_pickle': path, 'entity_aware': True,
+                       'sampling_strategy': 'unseen', 'num_negative_samples': 4, 'cf_loss_type': 'BPR'})
+    assert isinstance(ds, ProcessedHIN) and ds['num_nodes'] == src.num_nodes and ds.num_uids == src.num_uids
+    assert ds.iid_feat_nids == src.iid_feat_nids and ds.uid_feat_nids == src.uid_feat_nids
+    a = update_pea_graph_input({'dataset': 'Movielens', 'name': 'latest-small'}, {'device': 'cpu'}, src)
+    b = update_pea_graph_input({'dataset': 'Movielens', 'name': 'latest-small'}, {'device': 'cpu'}, ds)
+    assert all(torch.equal(x, y) for pa, pb in zip(a, b) for x, y in zip(pa, pb))
+    batches = []
+    for d in (src, ds):
+        osolver.seed_everything(3)
+        d.cf_negative_sampling()
+        batches.append(d.get_batch(list(range(50))))
+    assert torch.equal(batches[0], batches[1]) and batches[0].shape == (50, 9)
