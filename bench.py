@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument('--model', default='gcn', choices=['gcn', 'gat', 'sage'])
     ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-cuda-graph', action='store_true', help='launch every kernel eagerly instead of replaying the captured step')
     ap.add_argument('--breakdown', action='store_true', help='extra untimed pass: ms per C-ABI entry point')
     ap.add_argument('--prewarm', type=float, default=2.0, help='seconds of untimed steps before the warm-up')
     return ap.parse_args()
@@ -221,7 +222,8 @@ def run_product(args):
     torch.manual_seed(2020)
     model = product_model_for(ds, args.model, device=dev)
     params = [p for p in model.parameters()]
-    opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-3, fused=True)
+    use_graph = not args.no_cuda_graph
+    opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-3, fused=True, capturable=use_graph)
     model.train()
     K, W, B = args.steps, args.warmup, args.batch
     host_batches = make_batches(ds, B, K + W, seed=100 + rank).pin_memory()
@@ -238,13 +240,15 @@ def run_product(args):
             from graph_recsys_benchmark_b200.distributed import allreduce_gradients
             allreduce_gradients(params)
 
-    def step(batch):
+    def eager_step(batch):
         opt.zero_grad(set_to_none=True)
         loss = model.loss(batch)
         loss.backward()
         allreduce_grads()
         opt.step()
         return loss
+
+    step = eager_step
 
     def barrier():
         torch.cuda.synchronize()
@@ -266,6 +270,23 @@ def run_product(args):
             dist.all_reduce(spin, op=dist.ReduceOp.MIN)       # every rank leaves the loop together
     for gr in opt.param_groups:
         gr['lr'] = 1e-3
+    graphed = None
+    if use_graph:
+        # the whole step (loss, backward, gradient all-reduce, Adam) replayed as one CUDA graph (graphed.py);
+        # every rank captures or none does, so a failed capture falls back to eager launches everywhere
+        from graph_recsys_benchmark_b200.graphed import GraphedTrainStep
+        ok = torch.ones(1, device=dev)
+        try:
+            graphed = GraphedTrainStep(model, opt, dev_batches[0], allreduce=allreduce_grads if world > 1 else None)
+        except Exception as exc:                                  # noqa: BLE001
+            sys.stderr.write('CUDA graph capture failed (%s: %s); running eager\n' % (type(exc).__name__, exc))
+            ok.zero_()
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 0.5:
+            graphed = None
+        else:
+            step = graphed
     for k in range(W):
         step(dev_batches[k])
     barrier()
@@ -275,7 +296,7 @@ def run_product(args):
     # (single GPU: inside the timed region - the step is GPU-bound and the events are free; multi-GPU:
     # the step is launch-bound and the extra event records slow it down by up to 2x, so the same
     # events are taken in an identical extra pass right after the timed one)
-    profile_in_timed = world == 1 and not os.environ.get('PEAGNN_BENCH_NO_PROFILE')
+    profile_in_timed = world == 1 and graphed is None and not os.environ.get('PEAGNN_BENCH_NO_PROFILE')
     F_.PROFILE = [] if profile_in_timed else None
     launches0 = _lib.load().peagnn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -289,6 +310,8 @@ def run_product(args):
         host_ms = (time.perf_counter() - t_host) * 1e3 / K       # time the host needs to ENQUEUE a step
         barrier()
     launches = int(_lib.load().peagnn_launch_count() - launches0)
+    if graphed is not None:
+        launches = graphed.launches_per_replay * K                # replays do not pass through the C ABI's counter
     ms_total = e0.elapsed_time(e1)
     prof_spmm = F_.PROFILE or []
     F_.PROFILE = None
@@ -297,7 +320,7 @@ def run_product(args):
         K_roof = min(K, 10)
         F_.PROFILE = []
         for k in range(K_roof):
-            step(dev_batches[W + k])
+            eager_step(dev_batches[W + k])                         # eager: events cannot be read out of a graph
         barrier()
         prof_spmm = F_.PROFILE
         F_.PROFILE = None
@@ -308,8 +331,11 @@ def run_product(args):
     t_e2e[0].record()
     last = 0.0
     for k in range(K):
-        b = host_batches[W + k].to(dev, non_blocking=True)        # H2D inside the timed region
-        last = step(b).item()                                      # D2H read of the loss every step
+        if graphed is not None:
+            last = graphed(host_batches[W + k]).item()             # H2D into the graph's batch + D2H loss read, every step
+        else:
+            b = host_batches[W + k].to(dev, non_blocking=True)    # H2D inside the timed region
+            last = step(b).item()                                  # D2H read of the loss every step
     t_e2e[1].record()
     barrier()
     ms_e2e = t_e2e[0].elapsed_time(t_e2e[1])
@@ -320,7 +346,7 @@ def run_product(args):
         K_prof = min(K, 5)
         _lib.profile = []
         for k in range(K_prof):
-            step(dev_batches[W + k])
+            eager_step(dev_batches[W + k])
         barrier()
         prof_all = _lib.profile
         _lib.profile = None
@@ -371,6 +397,7 @@ def run_product(args):
             'e2e': {'value': world * B * K / (ms_e2e * 1e-3), 'unit': 'triples/s', 'h2d_bytes_per_step': B * 3 * 8,
                     'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / K, 'last_loss': last},
             'gpu_launches': launches, 'host_enqueue_ms_per_step': host_ms,
+            'cuda_graph': graphed is not None,
             'roofline': {'bound': 'hbm', 'kernel': agg_name + ' (csr_rows_kernel / csr_chunk_kernel)',
                          'achieved': achieved, 'peak': hbm_peak, 'peak_source': peak_src, 'unit': 'GB/s',
                          'frac': (achieved / hbm_peak) if achieved else None,

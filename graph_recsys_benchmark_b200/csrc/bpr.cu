@@ -11,6 +11,11 @@ extern "C" int peagnn_linear_wgrad(const float*, int64_t, const float*, int64_t,
                                    peagnn_stream_t);
 extern "C" size_t peagnn_wgrad_workspace_floats(int64_t, int32_t, int32_t);
 
+// The fc1 loops are unrolled completely for the shipped repr_dim (16) and below; wider layers keep the
+// inner loop unrolled only (complete unrolling of 64 x 64 x 3 FMAs takes ptxas minutes for no gain).
+template <int D>
+constexpr int kOuterUnroll = D <= 16 ? D : 1;
+
 template <int D>
 struct FcSmem {
   float w1[D * 2 * D];  // [D][2D] (out, in)
@@ -40,7 +45,7 @@ __device__ __forceinline__ void load_row(const float* repr, int64_t ldr, int64_t
 // hu[j] = b1[j] + sum_k W1[j][k] u[k]           (user half of fc1, shared by pos and neg)
 template <int D>
 __device__ __forceinline__ void user_half(const FcSmem<D>& s, const float* u, float* hu) {
-#pragma unroll
+#pragma unroll(kOuterUnroll<D>)
   for (int j = 0; j < D; ++j) {
     float a = s.b1[j];
 #pragma unroll
@@ -52,7 +57,7 @@ __device__ __forceinline__ void user_half(const FcSmem<D>& s, const float* u, fl
 template <int D>
 __device__ __forceinline__ float item_score(const FcSmem<D>& s, const float* hu, const float* it, float* pre) {
   float sc = s.b2;
-#pragma unroll
+#pragma unroll(kOuterUnroll<D>)
   for (int j = 0; j < D; ++j) {
     float a = hu[j];
 #pragma unroll
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(128) bpr_kernel(const float* __restrict__ repr
   float du[D], dp[D], dn[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) du[k] = dp[k] = dn[k] = 0.f;
-#pragma unroll
+#pragma unroll(kOuterUnroll<D>)
   for (int j = 0; j < D; ++j) {
     const float dhp = pre_p[j] > 0.f ? g * s.w2[j] : 0.f;
     const float dhn = pre_n[j] > 0.f ? -g * s.w2[j] : 0.f;

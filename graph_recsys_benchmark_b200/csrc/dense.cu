@@ -7,6 +7,9 @@
 #include <algorithm>
 #include "common.cuh"
 #include "dense_v2.cuh"
+#include "dense_tc.cuh"
+#include "dense_umma.cuh"
+#include <stdlib.h>
 
 namespace peagnn {
 
@@ -307,6 +310,22 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int n_p
   }
 }
 
+// PEAGNN_DENSE selects the projection kernels for the hot shapes (A/B timing): "ffma" = fp32 pipe
+// (dense_v2.cuh), "mma" = mma.sync 3xTF32 (dense_tc.cuh), "umma" = tcgen05 3xTF32 (dense_umma.cuh);
+// default: tcgen05 where the output is 64 wide, mma.sync for the narrower outputs (measured per shape,
+// profiles/r1_dense_tensor_cores.md).
+static int dense_mode() {
+  static const int mode = [] {
+    const char* e = getenv("PEAGNN_DENSE");
+    if (e && e[0] == 'f') return 0;
+    if (e && e[0] == 'm') return 1;
+    if (e && e[0] == 'u') return 2;
+    return 3;
+  }();
+  return mode;
+}
+static bool use_tensor_cores() { return dense_mode() != 0; }
+
 static int wgrad_parts(int64_t n_rows) {
   const int64_t by_rows = (n_rows + 255) / 256;
   return (int)imax64(1, imin64(by_rows, (int64_t)kNumSMs * 2));
@@ -455,6 +474,31 @@ extern "C" int peagnn_linear(const float* X, int64_t ldx, const float* mask, int
                      (!out_mask || (aligned16(out_mask) && ldom % 4 == 0 && ldom >= M)),
                  "peagnn_linear: pointers must be 16-byte aligned");
   if (n == 0) return PEAGNN_OK;
+  // hot shapes without an input gate: 3xTF32 tensor-core kernels (dense_tc.cuh); PEAGNN_DENSE=ffma keeps
+  // the fp32-pipe kernels for A/B timing
+  if (!mask && (dense_mode() == 2 || (dense_mode() == 3 && M == 64)) && (K == 16 || K == 32 || K == 64) &&
+      (M == 16 || M == 32 || M == 64)) {
+#define PEAGNN_LINUM(K_, N_) \
+  return launch_linear_umma<K_, N_>(X, ldx, n, W, w_is_out_in, bias, relu, accumulate, Y, ldy, out_mask, ldom, stream)
+#define PEAGNN_LINUM_K(K_) \
+  do { if (M == 16) PEAGNN_LINUM(K_, 16); if (M == 32) PEAGNN_LINUM(K_, 32); PEAGNN_LINUM(K_, 64); } while (0)
+    if (K == 16) PEAGNN_LINUM_K(16);
+    if (K == 32) PEAGNN_LINUM_K(32);
+    PEAGNN_LINUM_K(64);
+#undef PEAGNN_LINUM_K
+#undef PEAGNN_LINUM
+  }
+  if (!mask && use_tensor_cores() && (K == 16 || K == 32 || K == 64) && (M == 16 || M == 32 || M == 64)) {
+#define PEAGNN_LINTC(K_, MT_) \
+  return launch_linear_tc<K_, MT_>(X, ldx, n, W, w_is_out_in, bias, relu, accumulate, Y, ldy, out_mask, ldom, stream)
+#define PEAGNN_LINTC_K(K_) \
+  do { if (M == 16) PEAGNN_LINTC(K_, 2); if (M == 32) PEAGNN_LINTC(K_, 4); PEAGNN_LINTC(K_, 8); } while (0)
+    if (K == 16) PEAGNN_LINTC_K(16);
+    if (K == 32) PEAGNN_LINTC_K(32);
+    PEAGNN_LINTC_K(64);
+#undef PEAGNN_LINTC_K
+#undef PEAGNN_LINTC
+  }
   const int tx = pow2_ge(M / 4);
   if ((K == 64 || K == 16) && tx <= 16) {   // hot shapes: prefetching register-tile kernels
 #define PEAGNN_LIN2(K_, TX_, RPT_) \
@@ -505,6 +549,17 @@ extern "C" int peagnn_linear_wgrad(const float* X, int64_t ldx, const float* dY,
     if (dW && KM) cudaMemsetAsync(dW, 0, sizeof(float) * KM, stream);
     if (db) cudaMemsetAsync(db, 0, sizeof(float) * M, stream);
     return check_launch("peagnn_linear_wgrad(memset)");
+  }
+  if (use_tensor_cores() && ((K == 64 && (M == 64 || M == 32 || M == 16)) || (K == 16 && M == 64))) {
+    const int64_t rpc = ((n + parts - 1) / parts + kTcWgRows - 1) / kTcWgRows * kTcWgRows;
+    int rc2;
+    if (K == 16) rc2 = launch_wgrad_tc<16, 64>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
+    else if (M == 64) rc2 = launch_wgrad_tc<64, 64>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
+    else if (M == 32) rc2 = launch_wgrad_tc<64, 32>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
+    else rc2 = launch_wgrad_tc<64, 16>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
+    if (rc2) return rc2;
+    wgrad_finalize_v2_kernel<<<(KM + M + 63) / 64, 256, 0, stream>>>(workspace, parts, K, M, w_is_out_in, dW, db);
+    return check_launch("peagnn_linear_wgrad(tc stage2)");
   }
   if (K == 64 && (M == 64 || M == 32 || M == 16)) {   // hot shapes
     const int64_t rpc = ((n + parts - 1) / parts + kWg2Rows - 1) / kWg2Rows * kWg2Rows;

@@ -1,0 +1,259 @@
+// tcgen05 projection kernel for the hot shapes of the PEAGNN channels:  Y = act(X @ W + b (+ Y)).
+//
+// fp32 in / fp32 out with fp32-level accuracy on the 5th-generation tensor cores: every operand is
+// split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and the product is issued as three chains of
+// tcgen05.mma.kind::tf32 (lo*hi, hi*lo, hi*hi - small terms first) into one fp32 accumulator in
+// tensor memory ("3xTF32", error ~2^-22 per product; parity tests keep their 1e-5 bound).
+//
+// One CTA owns a 128-row tile at a time (UMMA M = 128, N = all output columns, K = 8 per instruction):
+//   * W is split once per CTA into B_hi / B_lo, kept in shared memory for the CTA's lifetime;
+//   * the X tile is prefetched into registers one tile ahead, split, and written as A_hi / A_lo in the
+//     canonical no-swizzle K-major core-matrix layout (8 rows x 16 bytes per core matrix; consecutive
+//     8-row groups 128 B apart, consecutive 16-byte K chunks (BM/8)*128 B apart);
+//   * one thread issues the 3 * K/8 MMAs and commits them to an mbarrier; all 8 warps then read the
+//     accumulator back (tcgen05.ld 32x32b: warp w owns TMEM lanes 32*(w%4).., half of the columns),
+//     apply bias / accumulate / relu / relu-backward gate and store.
+// Two CTAs are resident per SM, so one CTA's split + epilogue overlaps the other's loads and MMAs; there
+// is no warp specialisation inside a CTA.  Layout / descriptor bit fields follow the PTX ISA's tcgen05
+// shared-memory and instruction descriptors.
+#pragma once
+#include "common.cuh"
+#include "dense_tc.cuh"   // split_tf32
+
+namespace peagnn {
+
+constexpr int kUmThreads = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor: no swizzle, K-major; addresses / offsets in 16-byte units
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;      // K direction: next 16-byte chunk of the same rows
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;      // M/N direction: next group of 8 rows
+  d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)
+  return d;                                   // base offset 0, layout type 0 = SWIZZLE_NONE
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();   // a lost MMA completion must fail the launch, not hang the device
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int K, int N>
+__global__ void __launch_bounds__(kUmThreads, 2) linear_umma_kernel(
+    const float* __restrict__ X, int64_t ldx, int64_t n_rows, const float* __restrict__ W, int w_is_out_in,
+    const float* __restrict__ bias, int relu, int accumulate, float* __restrict__ Y, int64_t ldy,
+    const float* __restrict__ out_mask, int64_t ldom) {
+  constexpr int BM = 128;
+  constexpr int KC = K / 4;                     // 16-byte chunks along K
+  constexpr int KS = K / 8;                     // MMA k-steps
+  constexpr int CG = KC / 4;                    // chunk groups of 4 (one warp load covers 8 rows x 4 chunks)
+  constexpr int ITS = 2 * CG;                   // (8 rows x 4 chunks) blocks per warp per tile
+  constexpr uint32_t A_SBO = 128, A_LBO = (BM / 8) * 128;
+  constexpr uint32_t B_SBO = 128, B_LBO = (N / 8) * 128;
+  constexpr int A_BYTES = BM * K * 4, B_BYTES = N * K * 4;
+  constexpr uint32_t TMEM_COLS = N < 32 ? 32 : N;
+  constexpr int CW = N / 2;                     // output columns per warp in the epilogue
+  constexpr int SP = CW + 4;                    // staging row pitch (floats): 16-byte stores stay conflict-free
+  constexpr int STAGE_BYTES = 8 * 32 * SP * 4;  // epilogue staging, overlaid on the A buffers
+  constexpr int A_REGION = 2 * A_BYTES > STAGE_BYTES ? 2 * A_BYTES : STAGE_BYTES;
+  static_assert(K % 16 == 0 && N % 16 == 0 && N <= 256 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "unsupported shape");
+  // instruction descriptor: D = f32, A = B = tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  extern __shared__ __align__(128) uint8_t umma_smem[];
+  uint8_t* sAh = umma_smem;
+  uint8_t* sAl = sAh + A_BYTES;
+  uint8_t* sBh = sAh + A_REGION;
+  uint8_t* sBl = sBh + B_BYTES;
+  __shared__ __align__(8) uint64_t mma_done;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rsub = lane & 7, csub = lane >> 3;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 32) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mma_done)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // B = W^T as an N x K, K-major operand: element (n, k) = W[k][n]
+  for (int idx = threadIdx.x; idx < N * KC; idx += kUmThreads) {
+    const int j = idx / N, n = idx - j * N;
+    float w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      w[e] = w_is_out_in ? __ldg(W + (size_t)n * K + 4 * j + e) : __ldg(W + (size_t)(4 * j + e) * N + n);
+    uint4 hi, lo;
+    split_tf32(w[0], hi.x, lo.x); split_tf32(w[1], hi.y, lo.y);
+    split_tf32(w[2], hi.z, lo.z); split_tf32(w[3], hi.w, lo.w);
+    const uint32_t off = (uint32_t)(j * (N / 8) + (n >> 3)) * 128u + (uint32_t)(n & 7) * 16u;
+    *reinterpret_cast<uint4*>(sBh + off) = hi;
+    *reinterpret_cast<uint4*>(sBl + off) = lo;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t bar = smem_u32(&mma_done);
+  const uint32_t aH = smem_u32(sAh), aL = smem_u32(sAl), bH = smem_u32(sBh), bL = smem_u32(sBl);
+
+  const int64_t n_tiles = (n_rows + BM - 1) / BM;
+  float4 pre[ITS];
+  auto fetch = [&](int64_t tile) {
+#pragma unroll
+    for (int it = 0; it < ITS; ++it) {
+      const int b = warp * ITS + it;
+      const int64_t row = tile * BM + 8 * (b / CG) + rsub;
+      const int chunk = 4 * (b % CG) + csub;
+      pre[it] = row < n_rows ? ldg4(X + row * ldx + 4 * chunk) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+
+  uint32_t phase = 0;
+  int64_t tile = blockIdx.x;
+  if (tile < n_tiles) fetch(tile);
+  for (; tile < n_tiles; tile += gridDim.x) {
+    // split this tile into A_hi / A_lo (the previous tile's MMAs were waited for by every thread)
+#pragma unroll
+    for (int it = 0; it < ITS; ++it) {
+      const int b = warp * ITS + it;
+      const int i = b / CG, chunk = 4 * (b % CG) + csub;
+      uint4 hi, lo;
+      split_tf32(pre[it].x, hi.x, lo.x); split_tf32(pre[it].y, hi.y, lo.y);
+      split_tf32(pre[it].z, hi.z, lo.z); split_tf32(pre[it].w, hi.w, lo.w);
+      const uint32_t off = (uint32_t)(chunk * (BM / 8) + i) * 128u + (uint32_t)rsub * 16u;
+      *reinterpret_cast<uint4*>(sAh + off) = hi;
+      *reinterpret_cast<uint4*>(sAl + off) = lo;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the MMA
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // orders the previous tile's tcgen05.ld
+    __syncthreads();
+    const int64_t next = tile + gridDim.x;
+    if (next < n_tiles) fetch(next);   // in flight while the MMAs and the epilogue run
+
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t a0 = term == 0 ? aL : aH;
+        const uint32_t b0 = term == 1 ? bL : bH;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+          umma_tf32(tmem_base, umma_desc(a0 + ks * 2 * A_LBO, A_LBO, A_SBO), umma_desc(b0 + ks * 2 * B_LBO, B_LBO, B_SBO),
+                    IDESC, (term | ks) != 0);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // epilogue: warp w reads TMEM lanes 32 * (w % 4).. (one accumulator row per thread), columns
+    // [(w / 4) * CW, +CW), transposes its 32 x CW block through shared memory (the A buffers are free
+    // once the MMAs have completed) and finishes row-contiguous: full 32-byte sectors on every
+    // global access (a thread-per-row store would touch half sectors and make L2 fetch before write).
+    const int col0 = (warp >> 2) * CW;
+    const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0;
+    float* stage = reinterpret_cast<float*>(sAh) + warp * (32 * SP);
+    __syncwarp();   // lanes leave the mbarrier spin at different times; tcgen05.ld is warp-collective
+#pragma unroll
+    for (int u = 0; u < CW / 8; ++u) {
+      float v[8];
+      tmem_ld8(taddr + 8 * u, v);
+      st4(stage + lane * SP + 8 * u, make_float4(v[0], v[1], v[2], v[3]));
+      st4(stage + lane * SP + 8 * u + 4, make_float4(v[4], v[5], v[6], v[7]));
+    }
+    __syncwarp();
+    constexpr int C4 = CW / 4;                  // float4 per row segment
+    constexpr int RPI = 32 / C4;                // rows per warp instruction
+    const int c = col0 + 4 * (lane % C4);
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) bv = ldg4(bias + c);
+#pragma unroll
+    for (int it = 0; it < C4; ++it) {
+      const int r = it * RPI + lane / C4;
+      const int64_t row = tile * BM + 32 * (warp & 3) + r;
+      if (row < n_rows) {
+        float4 o = *reinterpret_cast<const float4*>(stage + r * SP + 4 * (lane % C4));
+        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+        float* yp = Y + row * ldy + c;
+        if (accumulate) {
+          const float4 p = *reinterpret_cast<const float4*>(yp);
+          o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+        }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (out_mask) {   // relu backward fused on the way out
+          const float4 g = ldg4(out_mask + row * ldom + c);
+          o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
+        }
+        st4(yp, o);
+      }
+    }
+    __syncthreads();   // staging lives in the A buffers: nobody may split the next tile into them yet
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+template <int K, int N>
+static int launch_linear_umma(const float* X, int64_t ldx, int64_t n, const float* W, int w_is_out_in,
+                              const float* bias, int relu, int accumulate, float* Y, int64_t ldy,
+                              const float* out_mask, int64_t ldom, cudaStream_t stream) {
+  constexpr size_t a_bytes = (size_t)2 * (128 * K * 4), stage_bytes = (size_t)8 * 32 * (N / 2 + 4) * 4;
+  constexpr size_t smem = (a_bytes > stage_bytes ? a_bytes : stage_bytes) + (size_t)2 * (N * K * 4) + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(linear_umma_kernel<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  const int64_t tiles = (n + 127) / 128;
+  const int blocks = (int)imin64(tiles, (int64_t)kNumSMs * 2);
+  linear_umma_kernel<K, N><<<blocks, kUmThreads, smem, stream>>>(X, ldx, n, W, w_is_out_in, bias, relu, accumulate,
+                                                                 Y, ldy, out_mask, ldom);
+  return check_launch("peagnn_linear(umma)");
+}
+
+}  // namespace peagnn

@@ -124,18 +124,28 @@ class BaseSolver(object):
         sync_every = self.train_args.get('loss_sync_every', 50)
         model.train()
         dataset.cf_negative_sampling()
-        losses, pending = [], []
+        losses, pending, graphed = [], [], None
         n_batches = (len(dataset) + self.train_args['batch_size'] - 1) // self.train_args['batch_size']
         train_bar = tqdm.tqdm(self._batches(dataset), total=n_batches, disable=self.train_args.get('quiet', False))
         for step, batch in enumerate(train_bar):
             if max_steps is not None and step >= max_steps:
                 break
             batch = batch.to(device, non_blocking=True)
-            optimizer.zero_grad()
-            loss = model.loss(batch)
-            loss.backward()
-            optimizer.step()
-            pending.append(loss.detach())
+            if self.train_args.get('cuda_graph', False) and step > 0:
+                # train_args['cuda_graph']: after one eager step the whole step is replayed as one CUDA graph
+                # (graphed.py; the optimizer must have been built with capturable=True)
+                if graphed is None:
+                    from .graphed import GraphedTrainStep
+                    graphed = GraphedTrainStep(model, optimizer, batch)    # trains on this batch, then captures
+                    pending.append(graphed.first_loss)
+                else:
+                    pending.append(graphed(batch).clone())
+            else:
+                optimizer.zero_grad()
+                loss = model.loss(batch)
+                loss.backward()
+                optimizer.step()
+                pending.append(loss.detach())
             if len(pending) >= sync_every:
                 losses.extend(torch.stack(pending).cpu().tolist())
                 pending = []
@@ -177,8 +187,9 @@ class BaseSolver(object):
                     model = self.model_class(**self.model_args).to(self.train_args['device'])
 
                     opt_class = get_opt_class(self.train_args['opt'])
+                    opt_kwargs = {'capturable': True} if self.train_args.get('cuda_graph', False) else {}
                     optimizer = opt_class(params=model.parameters(), lr=self.train_args['lr'],
-                                          weight_decay=self.train_args['weight_decay'])
+                                          weight_decay=self.train_args['weight_decay'], **opt_kwargs)
 
                     weights_path = os.path.join(self.train_args['weights_folder'], 'run_{}'.format(str(run)))
                     if not os.path.exists(weights_path):

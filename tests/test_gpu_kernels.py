@@ -302,3 +302,57 @@ def test_scoring_kernels_other_repr_dims(D):
     _, _, scores = F_.eval_rank(r.to(DEV), users.to(DEV), cand.to(DEV), 1, *[p.detach() for p in ps], return_scores=True)
     ref = f2(torch.relu(f1(torch.cat([r.double()[users].unsqueeze(1).expand(-1, 50, -1), r.double()[cand]], dim=-1)))).squeeze(-1)
     assert rel_err(scores, ref) < TOL
+
+
+# ---- projections called directly (tensor-core 3xTF32 kernels for the hot shapes, FFMA otherwise) ---------------
+@pytest.mark.parametrize('K,M', [(64, 64), (64, 16), (16, 64), (64, 32), (32, 32), (16, 16), (32, 64), (64, 48), (128, 16)])
+@pytest.mark.parametrize('n', [1, 127, 129, 5000])
+@pytest.mark.parametrize('variant', ['plain', 'out_in+bias+relu', 'accumulate+gate', 'in_mask'])
+def test_linear_direct(K, M, n, variant):
+    """peagnn_linear against an fp64 matmul, every epilogue flag, ragged row counts, strided operands."""
+    from graph_recsys_benchmark_b200 import functional as F_
+    g = torch.Generator().manual_seed(1000 * K + M + n)
+    Xw = torch.randn(n, K + 8, generator=g).cuda()
+    X = Xw[:, 4:4 + K]                                   # leading dimension > K
+    out_in = variant == 'out_in+bias+relu'
+    W = torch.randn((M, K) if out_in else (K, M), generator=g).cuda()
+    bias = torch.randn(M, generator=g).cuda() if variant != 'plain' else None
+    Y0 = torch.randn(n, M, generator=g).cuda()
+    gate = torch.randn(n, M, generator=g).cuda() if variant == 'accumulate+gate' else None
+    mask = torch.randn(n, K, generator=g).cuda() if variant == 'in_mask' else None
+    Y = Y0.clone()
+    F_.linear_raw(X, W, Y, out_in, bias, relu=out_in, accumulate=variant == 'accumulate+gate', mask=mask, out_mask=gate)
+    Xd = X.double() * (mask > 0).double() if mask is not None else X.double()
+    want = Xd @ (W.double().t() if out_in else W.double())
+    if bias is not None:
+        want = want + bias.double()
+    if variant == 'accumulate+gate':
+        want = (want + Y0.double()) * (gate > 0).double()
+    if out_in:
+        want = want.clamp_min(0)
+    assert rel_err(Y, want) < 1e-5                      # fp32 tolerance of the path (DESIGN.md section 5)
+    if variant == 'accumulate+gate':
+        assert bool((Y[gate <= 0] == 0).all())          # gated entries are exactly zero
+
+
+@pytest.mark.parametrize('K,M', [(64, 64), (64, 16), (16, 64), (64, 32), (32, 32), (16, 16), (128, 64)])
+@pytest.mark.parametrize('n', [1, 63, 4097, 40000])
+@pytest.mark.parametrize('masked,out_in', [(False, False), (True, True)])
+def test_wgrad_direct(K, M, n, masked, out_in):
+    """peagnn_linear_wgrad: dW = X^T gate(dY), db = colsum(gate(dY)) against fp64; run twice -> bit-identical."""
+    from graph_recsys_benchmark_b200 import functional as F_
+    g = torch.Generator().manual_seed(77 * K + M + n)
+    X = torch.randn(n, K, generator=g).cuda()
+    dY = torch.randn(n, M, generator=g).cuda()
+    mask = torch.randn(n, M, generator=g).cuda() if masked else None
+    outs = []
+    for _ in range(2):
+        dW = torch.full((M, K) if out_in else (K, M), float('nan'), device='cuda')
+        db = torch.full((M,), float('nan'), device='cuda')
+        F_.wgrad_raw(X, dY, K, M, out_in, dW, db, mask)
+        outs.append((dW, db))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    d = dY.double() * (mask > 0).double() if masked else dY.double()
+    want = X.double().t() @ d
+    assert rel_err(outs[0][0], want.t() if out_in else want) < 1e-5
+    assert rel_err(outs[0][1], d.sum(0)) < 1e-5

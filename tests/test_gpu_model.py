@@ -232,3 +232,48 @@ def test_product_matches_frozen_golden_vectors(kind):
     if torch.equal(ranks, g['ranks']):
         assert hr[5] == g['hr10'] and abs(nd[5] - g['ndcg10']) < 1e-12
     assert abs(auc[0] - g['auc']) < 2e-3 and abs(el[0] - g['eval_loss']) <= 1e-4 * abs(g['eval_loss'])
+
+
+@pytest.mark.parametrize('kind', ['gcn', 'sage', 'gat'])
+def test_cuda_graph_step_equals_eager_steps(kind):
+    """graphed.GraphedTrainStep: replaying the captured step (loss, backward, Adam) leaves the same weights
+    and losses as launching every kernel eagerly; a batch of another shape takes the eager path."""
+    import copy
+    from graph_recsys_benchmark_b200.graphed import GraphedTrainStep
+    ds = _dataset()
+    batches = [_batch(ds, 256, False, seed=i).to(DEV) for i in range(5)]
+    torch.manual_seed(5)
+    eager = product_model_for(ds, kind)
+    replay = product_model_for(ds, kind)
+    replay.load_state_dict(copy.deepcopy(eager.state_dict()))
+    losses = {}
+    for name, model in (('eager', eager), ('graph', replay)):
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3, fused=True, capturable=True)
+        model.train()
+        out = []
+
+        def one(b):
+            opt.zero_grad(set_to_none=True)
+            loss = model.loss(b)
+            loss.backward()
+            opt.step()
+            return loss.detach()
+        out.append(float(one(batches[0])))                      # the eager step the capture needs first
+        if name == 'graph':
+            stepper = GraphedTrainStep(model, opt, batches[1])  # trains on batches[1] eagerly, then captures
+            assert stepper.launches_per_replay > 20
+            out.append(float(stepper.first_loss))
+        else:
+            stepper = one
+            out.append(float(one(batches[1])))
+        for b in batches[2:]:
+            out.append(float(stepper(b)))
+        out.append(float(stepper(batches[0][:100])))             # other shape -> eager fallback inside the wrapper
+        losses[name] = out
+    # the scoring kernel scatters d_repr with float atomics, and Adam turns a last-bit gradient difference
+    # into an update difference of up to ~lr on near-zero gradients: weights agree to a fraction of one update
+    for a, b in zip(losses['eager'], losses['graph']):
+        assert abs(a - b) <= 1e-4 * abs(a), losses
+    for (n, p), (_, q) in zip(eager.named_parameters(), replay.named_parameters()):
+        assert float((p - q).abs().max()) < 2e-3, n          # 6 steps x lr 1e-3 is the largest possible drift
+        assert rel_err(q, p) < 5e-3, n

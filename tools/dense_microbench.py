@@ -28,6 +28,12 @@ def timeit(fn, iters=10):
     return float(np.median(ts))
 
 
+A = torch.randn(N, 64, device=dev)
+B = torch.empty_like(A)
+t = timeit(lambda: B.copy_(A))
+print('torch copy [N,64] fp32        %7.1f us  %7.1f GB/s' % (t * 1e3, 8 * N * 64 / t / 1e6))
+t = timeit(lambda: A.sum())
+print('torch sum  [N,64] fp32        %7.1f us  %7.1f GB/s' % (t * 1e3, 4 * N * 64 / t / 1e6))
 for K, M, masked in [(64, 64, False), (64, 64, True), (64, 16, False), (16, 64, False), (64, 32, False)]:
     X = torch.randn(N, K, device=dev)
     W = torch.randn(K, M, device=dev)
