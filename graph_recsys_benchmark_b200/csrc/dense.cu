@@ -550,6 +550,18 @@ extern "C" int peagnn_linear_wgrad(const float* X, int64_t ldx, const float* dY,
     if (db) cudaMemsetAsync(db, 0, sizeof(float) * M, stream);
     return check_launch("peagnn_linear_wgrad(memset)");
   }
+  if ((dense_mode() == 2 && ((K == 64 && (M == 64 || M == 32 || M == 16)) || (K == 16 && M == 64))) ||
+      (dense_mode() == 3 && K == 64 && M == 64)) {   // default: tcgen05 for the square shape, mma.sync below
+    const int64_t rpc = ((n + parts - 1) / parts + kUmWgRows - 1) / kUmWgRows * kUmWgRows;
+    int rc2;
+    if (K == 16) rc2 = launch_wgrad_umma<16, 64>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
+    else if (M == 64) rc2 = launch_wgrad_umma<64, 64>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
+    else if (M == 32) rc2 = launch_wgrad_umma<64, 32>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
+    else rc2 = launch_wgrad_umma<64, 16>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
+    if (rc2) return rc2;
+    wgrad_finalize_v2_kernel<<<(KM + M + 63) / 64, 256, 0, stream>>>(workspace, parts, K, M, w_is_out_in, dW, db);
+    return check_launch("peagnn_linear_wgrad(umma stage2)");
+  }
   if (use_tensor_cores() && ((K == 64 && (M == 64 || M == 32 || M == 16)) || (K == 16 && M == 64))) {
     const int64_t rpc = ((n + parts - 1) / parts + kTcWgRows - 1) / kTcWgRows * kTcWgRows;
     int rc2;

@@ -12,7 +12,8 @@
 //     8-row groups 128 B apart, consecutive 16-byte K chunks (BM/8)*128 B apart);
 //   * one thread issues the 3 * K/8 MMAs and commits them to an mbarrier; all 8 warps then read the
 //     accumulator back (tcgen05.ld 32x32b: warp w owns TMEM lanes 32*(w%4).., half of the columns),
-//     apply bias / accumulate / relu / relu-backward gate and store.
+//     transpose it through shared memory and apply bias / accumulate / relu / relu-backward gate on
+//     row-contiguous 128-bit accesses (a thread-per-row store, even 256 bits wide, measured slower).
 // Two CTAs are resident per SM, so one CTA's split + epilogue overlaps the other's loads and MMAs; there
 // is no warp specialisation inside a CTA.  Layout / descriptor bit fields follow the PTX ISA's tcgen05
 // shared-memory and instruction descriptors.
@@ -61,6 +62,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (ok) return;
   }
   __trap();   // a lost MMA completion must fail the launch, not hang the device
+}
+
+// x = hi + lo with both halves on the tf32 grid; round-to-nearest (ties away, as cvt.rna) done on the
+// bit pattern: add half an ulp of the 13 dropped bits, clear them.  x - hi is exact in fp32.
+__device__ __forceinline__ void split_tf32_fast(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
 }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
@@ -159,8 +167,8 @@ __global__ void __launch_bounds__(kUmThreads, 2) linear_umma_kernel(
       const int b = warp * ITS + it;
       const int i = b / CG, chunk = 4 * (b % CG) + csub;
       uint4 hi, lo;
-      split_tf32(pre[it].x, hi.x, lo.x); split_tf32(pre[it].y, hi.y, lo.y);
-      split_tf32(pre[it].z, hi.z, lo.z); split_tf32(pre[it].w, hi.w, lo.w);
+      split_tf32_fast(pre[it].x, hi.x, lo.x); split_tf32_fast(pre[it].y, hi.y, lo.y);
+      split_tf32_fast(pre[it].z, hi.z, lo.z); split_tf32_fast(pre[it].w, hi.w, lo.w);
       const uint32_t off = (uint32_t)(chunk * (BM / 8) + i) * 128u + (uint32_t)rsub * 16u;
       *reinterpret_cast<uint4*>(sAh + off) = hi;
       *reinterpret_cast<uint4*>(sAl + off) = lo;
@@ -184,8 +192,9 @@ __global__ void __launch_bounds__(kUmThreads, 2) linear_umma_kernel(
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     }
-    mbar_wait(bar, phase);
+    if (warp == 0) mbar_wait(bar, phase);   // one warp polls; the others sleep at the barrier
     phase ^= 1;
+    __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // epilogue: warp w reads TMEM lanes 32 * (w % 4).. (one accumulator row per thread), columns
@@ -254,6 +263,201 @@ static int launch_linear_umma(const float* X, int64_t ldx, int64_t n, const floa
   linear_umma_kernel<K, N><<<blocks, kUmThreads, smem, stream>>>(X, ldx, n, W, w_is_out_in, bias, relu, accumulate,
                                                                  Y, ldy, out_mask, ldom);
   return check_launch("peagnn_linear(umma)");
+}
+
+// -------------------------------------------------------------------------------------------------
+// Weight gradient on tcgen05:  dW[K, M] = X^T @ gate(dY),  db = colsum(gate(dY)).
+//
+// The reduction runs over data rows, 64 per staged tile (8 MMA k-steps of 8 rows).  Operands are the
+// TRANSPOSED tiles, both K-major in the MMA's sense (contiguous along the data-row index):
+//   A = X^T  : UMMA M = 128 rows = the K features of X (rows K..127 are zero padding, written once),
+//   B = dY^T : UMMA N = M rows.
+// A thread loads a 4-row x 4-column block (four float4, rows fully coalesced), and the transposition is
+// free: chunk e of the block is (r0[e], r1[e], r2[e], r3[e]) - one 16-byte store per feature.  Groups of
+// 8 features are 144 B apart (not 128) so the eight stores of a quarter warp hit eight different bank quads.
+// The accumulator is read back after EVERY tile and added into fp32 registers (the tensor core's adder
+// never sees a long chain; same policy as wgrad_tc); per-CTA partials go to the workspace, stage 2 is
+// wgrad_finalize_v2_kernel.  Deterministic: no atomics anywhere.
+constexpr int kUmWgRows = 64;
+
+template <int K, int M, bool HAS_MASK>
+__global__ void __launch_bounds__(kUmThreads, 2) wgrad_umma_kernel(
+    const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY, int64_t ldd,
+    const float* __restrict__ mask, int64_t ldm, int64_t n_rows, int64_t rows_per_cta,
+    float* __restrict__ partial /* [grid][K*M + M] */) {
+  constexpr int KQ = K / 4, MQ = M / 4;                  // column quads of X / dY
+  constexpr int KCH = kUmWgRows / 4;                     // 16-byte chunks along the reduction (4 data rows each)
+  constexpr uint32_t SBO = 144;                          // 8-feature group pitch
+  constexpr uint32_t A_LBO = 16 * SBO, B_LBO = (M / 8) * SBO;
+  constexpr int A_BYTES = KCH * A_LBO, B_BYTES = KCH * B_LBO;
+  constexpr uint32_t TMEM_COLS = M < 32 ? 32 : M;
+  constexpr int CW = M / 2;                              // accumulator columns per warp
+  constexpr int KM = K * M;
+  static_assert(K % 16 == 0 && K <= 64 && M % 16 == 0 && M <= 64, "unsupported shape");
+  static_assert(KQ * KCH <= kUmThreads && MQ * KCH <= kUmThreads, "one 4x4 block per thread");
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(M >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  extern __shared__ __align__(128) uint8_t umma_smem[];
+  uint8_t* sAh = umma_smem;
+  uint8_t* sAl = sAh + A_BYTES;
+  uint8_t* sBh = sAl + A_BYTES;
+  uint8_t* sBl = sBh + B_BYTES;
+  __shared__ __align__(8) uint64_t mma_done;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 32) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mma_done)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 2 * A_BYTES / 16; i += kUmThreads)    // zero padding rows (and everything else) once
+    reinterpret_cast<uint4*>(sAh)[i] = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t bar = smem_u32(&mma_done);
+  const uint32_t aH = smem_u32(sAh), aL = smem_u32(sAl), bH = smem_u32(sBh), bL = smem_u32(sBl);
+
+  // this thread's 4x4 blocks: data rows 4*kc .. 4*kc+3 of the tile, columns 4*q .. 4*q+3
+  const bool has_x = threadIdx.x < KQ * KCH, has_d = threadIdx.x < MQ * KCH;
+  const int xq = threadIdx.x % KQ, xkc = threadIdx.x / KQ;
+  const int dq = threadIdx.x % MQ, dkc = threadIdx.x / MQ;
+
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r_end = imin64(n_rows, r_begin + rows_per_cta);
+
+  float4 px[4], pd[4];
+  auto fetch = [&](int64_t base) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      px[j] = pd[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int64_t rx = base + 4 * xkc + j, rd = base + 4 * dkc + j;
+      if (has_x && rx < r_end) px[j] = ldg4(X + rx * ldx + 4 * xq);
+      if (has_d && rd < r_end) {
+        float4 v = ldg4(dY + rd * ldd + 4 * dq);
+        if (HAS_MASK) {
+          const float4 gt = ldg4(mask + rd * ldm + 4 * dq);
+          v.x = gt.x > 0.f ? v.x : 0.f; v.y = gt.y > 0.f ? v.y : 0.f;
+          v.z = gt.z > 0.f ? v.z : 0.f; v.w = gt.w > 0.f ? v.w : 0.f;
+        }
+        pd[j] = v;
+      }
+    }
+  };
+  // chunk e of a 4x4 block = column e of its four rows; feature f lives in group f / 8, slot f % 8
+  auto store_block = [&](uint8_t* hi_base, uint8_t* lo_base, const float4 (&r)[4], int q, int kc, uint32_t lbo) {
+    const float c[4][4] = {{r[0].x, r[1].x, r[2].x, r[3].x}, {r[0].y, r[1].y, r[2].y, r[3].y},
+                           {r[0].z, r[1].z, r[2].z, r[3].z}, {r[0].w, r[1].w, r[2].w, r[3].w}};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int f = 4 * q + e;
+      uint4 hi, lo;
+      split_tf32_fast(c[e][0], hi.x, lo.x); split_tf32_fast(c[e][1], hi.y, lo.y);
+      split_tf32_fast(c[e][2], hi.z, lo.z); split_tf32_fast(c[e][3], hi.w, lo.w);
+      const uint32_t off = (uint32_t)kc * lbo + (uint32_t)(f >> 3) * SBO + (uint32_t)(f & 7) * 16u;
+      *reinterpret_cast<uint4*>(hi_base + off) = hi;
+      *reinterpret_cast<uint4*>(lo_base + off) = lo;
+    }
+  };
+
+  float master[CW];
+#pragma unroll
+  for (int i = 0; i < CW; ++i) master[i] = 0.f;
+  float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int col0 = (warp >> 2) * CW;
+  const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0;
+  const bool reads_acc = 32 * (warp & 3) < K;            // TMEM lanes K..127 hold the zero padding
+
+  uint32_t phase = 0;
+  if (r_begin < r_end) fetch(r_begin);
+  for (int64_t base = r_begin; base < r_end; base += kUmWgRows) {
+    if (has_x) store_block(sAh, sAl, px, xq, xkc, A_LBO);
+    if (has_d) {
+      store_block(sBh, sBl, pd, dq, dkc, B_LBO);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { bsum.x += pd[j].x; bsum.y += pd[j].y; bsum.z += pd[j].z; bsum.w += pd[j].w; }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (base + kUmWgRows < r_end) fetch(base + kUmWgRows);
+
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t a0 = term == 0 ? aL : aH;
+        const uint32_t b0 = term == 1 ? bL : bH;
+#pragma unroll
+        for (int ks = 0; ks < kUmWgRows / 8; ++ks)
+          umma_tf32(tmem_base, umma_desc(a0 + ks * 2 * A_LBO, A_LBO, SBO), umma_desc(b0 + ks * 2 * B_LBO, B_LBO, SBO),
+                    IDESC, (term | ks) != 0);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+    if (warp == 0) mbar_wait(bar, phase);
+    phase ^= 1;
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (reads_acc) {
+#pragma unroll
+      for (int u = 0; u < CW / 8; ++u) {
+        float v[8];
+        tmem_ld8(taddr + 8 * u, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) master[8 * u + e] += v[e];
+      }
+    }
+  }
+
+  // this CTA's partial: thread owns feature 32 * (warp % 4) + lane, columns [col0, col0 + CW)
+  float* dst = partial + (size_t)blockIdx.x * (KM + M);
+  const int f = 32 * (warp & 3) + lane;
+  if (reads_acc && f < K) {
+#pragma unroll
+    for (int u = 0; u < CW / 4; ++u)
+      st4(dst + (size_t)f * M + col0 + 4 * u, make_float4(master[4 * u], master[4 * u + 1], master[4 * u + 2], master[4 * u + 3]));
+  }
+  // bias gradient: per-thread column sums folded over the 16 row groups in a fixed order
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(sAh);            // [KCH][M]
+  if (has_d) st4(red + dkc * M + 4 * dq, bsum);
+  __syncthreads();
+  if (threadIdx.x < M) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < KCH; ++r) s += red[r * M + threadIdx.x];
+    dst[KM + threadIdx.x] = s;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+template <int K, int M>
+static int launch_wgrad_umma(const float* X, int64_t ldx, const float* dY, int64_t ldd, const float* mask,
+                             int64_t ldm, int64_t n, int parts, int64_t rows_per_cta, float* workspace,
+                             cudaStream_t stream) {
+  constexpr size_t smem = (size_t)2 * (kUmWgRows / 4) * 144 * (16 + M / 8) + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(wgrad_umma_kernel<K, M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(wgrad_umma_kernel<K, M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  if (mask)
+    wgrad_umma_kernel<K, M, true><<<parts, kUmThreads, smem, stream>>>(X, ldx, dY, ldd, mask, ldm, n, rows_per_cta, workspace);
+  else
+    wgrad_umma_kernel<K, M, false><<<parts, kUmThreads, smem, stream>>>(X, ldx, dY, ldd, mask, ldm, n, rows_per_cta, workspace);
+  return check_launch("peagnn_linear_wgrad(umma)");
 }
 
 }  // namespace peagnn

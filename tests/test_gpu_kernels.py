@@ -307,7 +307,7 @@ def test_scoring_kernels_other_repr_dims(D):
 # ---- projections called directly (tensor-core 3xTF32 kernels for the hot shapes, FFMA otherwise) ---------------
 @pytest.mark.parametrize('K,M', [(64, 64), (64, 16), (16, 64), (64, 32), (32, 32), (16, 16), (32, 64), (64, 48), (128, 16)])
 @pytest.mark.parametrize('n', [1, 127, 129, 5000])
-@pytest.mark.parametrize('variant', ['plain', 'out_in+bias+relu', 'accumulate+gate', 'in_mask'])
+@pytest.mark.parametrize('variant', ['plain', 'out_in+bias+relu', 'accumulate+gate', 'in_mask', 'narrow_out'])
 def test_linear_direct(K, M, n, variant):
     """peagnn_linear against an fp64 matmul, every epilogue flag, ragged row counts, strided operands."""
     from graph_recsys_benchmark_b200 import functional as F_
@@ -321,6 +321,8 @@ def test_linear_direct(K, M, n, variant):
     gate = torch.randn(n, M, generator=g).cuda() if variant == 'accumulate+gate' else None
     mask = torch.randn(n, K, generator=g).cuda() if variant == 'in_mask' else None
     Y = Y0.clone()
+    if variant == 'narrow_out':                          # rows only 16-byte aligned: the 128-bit epilogue path
+        Y = torch.zeros(n, M + 4, device='cuda')[:, 4:]
     F_.linear_raw(X, W, Y, out_in, bias, relu=out_in, accumulate=variant == 'accumulate+gate', mask=mask, out_mask=gate)
     Xd = X.double() * (mask > 0).double() if mask is not None else X.double()
     want = Xd @ (W.double().t() if out_in else W.double())
