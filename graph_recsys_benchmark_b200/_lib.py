@@ -28,6 +28,7 @@ class CsrView(C.Structure):
 
 
 _P, _I32, _I64, _INT, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_int, C.c_float, C.c_size_t
+_U64 = C.c_uint64
 _G = C.POINTER(CsrView)
 
 # name -> (restype, argtypes); every name here must be declared in include/peagnn.h
@@ -62,6 +63,8 @@ SIGNATURES = {
     'peagnn_entity_reg': (_INT, [_P, _I64, _I32, _P, _I64, _F, _P, _INT, _P, _I64, _P, _SZ, _P]),
     'peagnn_eval_rank': (_INT, [_P, _I64, _I32, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     'peagnn_column_mean': (_INT, [_P, _I64, _I64, _I32, _P, _P, _SZ, _P]),
+    'peagnn_bpr_rows': (_INT, [_P, _I64, _P, _I64, _I32, _U64, _U64, _I32, _I64, _I64, _I64, _P, _P, _I32,
+                               _P, _P, _P, _P, _P, _I32, _P, _P]),
 }
 
 _lib = None

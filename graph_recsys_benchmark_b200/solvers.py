@@ -119,14 +119,33 @@ class BaseSolver(object):
             yield dataset.get_batch(indices) if hasattr(dataset, 'get_batch') else \
                 torch.stack([dataset[i] for i in indices], dim=0)
 
+    def _device_sampler(self, dataset, device, run):
+        key = (id(dataset), str(device), run)
+        cached = getattr(self, '_sampler_cache', None)
+        if cached is None or cached[0] != key:
+            from .sampling import DeviceBprSampler
+            self._sampler_cache = cached = (key, DeviceBprSampler(dataset, device, seed=2019 + run))
+        return cached[1]
+
     def train_epoch(self, run, epoch, model, optimizer, dataset, max_steps=None):
         device = self.train_args['device']
         sync_every = self.train_args.get('loss_sync_every', 50)
         model.train()
-        dataset.cf_negative_sampling()
         losses, pending, graphed = [], [], None
-        n_batches = (len(dataset) + self.train_args['batch_size'] - 1) // self.train_args['batch_size']
-        train_bar = tqdm.tqdm(self._batches(dataset), total=n_batches, disable=self.train_args.get('quiet', False))
+        bs = self.train_args['batch_size']
+        if self.train_args.get('device_sampling', False):
+            # train_args['device_sampling']: negatives and entity columns are drawn on the GPU (sampling.py);
+            # same distributions as the host loops below, but not the reference's host RNG stream
+            sampler = self._device_sampler(dataset, device, run)
+            order = sampler.permutation(epoch)
+            n_rows = len(sampler)
+            batches = (sampler.rows(order[s:s + bs], epoch) for s in range(0, n_rows, bs))
+        else:
+            dataset.cf_negative_sampling()
+            n_rows = len(dataset)
+            batches = self._batches(dataset)
+        n_batches = (n_rows + bs - 1) // bs
+        train_bar = tqdm.tqdm(batches, total=n_batches, disable=self.train_args.get('quiet', False))
         for step, batch in enumerate(train_bar):
             if max_steps is not None and step >= max_steps:
                 break

@@ -244,6 +244,27 @@ int peagnn_eval_rank(const float* repr, int64_t ldr, int32_t D, const int64_t* u
 int peagnn_column_mean(const double* A, int64_t lda, int64_t num_rows, int32_t cols, double* out,
                        double* workspace, size_t workspace_doubles, peagnn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K8: BPR training rows assembled on the device (replaces the host loops of
+ * datasets/movielens.py:920-940 (cf_negative_sampling, BPR branch) and :1153-1177 (entity-aware columns
+ * of __getitem__) when train_args['device_sampling'] is set).
+ * Row r of the epoch's unshuffled [E * num_neg, cols] table - interaction r / num_neg of user2item
+ * ([2, E] int64, row 0 = user nid, row 1 = item nid) plus its sampled columns - is a pure function of
+ * (seed, epoch, r): Philox4x32-10 keyed by seed, counter (r, epoch, draw).  out is int64 [B, cols],
+ * cols = 3: [u, pos, neg];  cols = 9: + [e+_i, e-_i, mask_i, e+_u, e-_u, mask_u].
+ * strategy 0 ("random"): neg uniform over [item_lo, item_lo + num_items);
+ * strategy 1 ("unseen"): neg uniform over the items not in the user's train set; seen_ptr [U + 1] /
+ *   seen_items are a CSR over users (u - user_lo) of their train item nids, ascending and unique.
+ * ifeat_* / ufeat_*: CSR over items / users of their feature node ids; type_starts [num_types + 1]:
+ *   ascending first node id of every node type, then num_nodes.  Unused tables may be NULL.
+ * ---------------------------------------------------------------------------------------- */
+int peagnn_bpr_rows(const int64_t* row_ids, int64_t B, const int64_t* u2i, int64_t E, int32_t num_neg,
+                    uint64_t seed, uint64_t epoch, int32_t strategy, int64_t user_lo, int64_t item_lo,
+                    int64_t num_items, const int64_t* seen_ptr, const int64_t* seen_items, int32_t cols,
+                    const int64_t* ifeat_ptr, const int64_t* ifeat_nids, const int64_t* ufeat_ptr,
+                    const int64_t* ufeat_nids, const int64_t* type_starts, int32_t num_types,
+                    int64_t* out, peagnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -277,3 +277,48 @@ def test_cuda_graph_step_equals_eager_steps(kind):
     for (n, p), (_, q) in zip(eager.named_parameters(), replay.named_parameters()):
         assert float((p - q).detach().abs().max()) < 2e-3, n          # 6 steps x lr 1e-3 is the largest possible drift
         assert rel_err(q, p) < 5e-3, n
+
+
+@pytest.mark.parametrize('shape,strategy,entity_aware', [('tiny', 'random', False), ('tiny', 'unseen', True),
+                                                         ('ml-small', 'unseen', False), ('ml-small', 'random', True)])
+def test_device_sampler_rows_equal_cpu_mirror(shape, strategy, entity_aware):
+    """peagnn_bpr_rows against oracle/device_sampler.py: integer rows, bit-exact."""
+    from oracle import device_sampler as ods
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+    from graph_recsys_benchmark_b200.sampling import DeviceBprSampler
+    ds = SyntheticHIN(shape, seed=7, entity_aware=entity_aware, sampling_strategy=strategy)
+    smp = DeviceBprSampler(ds, DEV, seed=(1 << 40) + 12345)
+    h = smp.host
+    n = len(smp)
+    ids = np.unique(np.concatenate([np.arange(min(n, 3000)), np.random.RandomState(0).randint(0, n, 3000), [n - 1]]))
+    got = smp.rows(torch.from_numpy(ids), epoch=5).cpu().numpy()
+    want = ods.bpr_rows(ids, h['u2i'], num_neg=smp.num_neg, seed=smp.seed, epoch=5, strategy=smp.strategy,
+                        user_lo=smp.user_lo, item_lo=smp.item_lo, num_items=smp.num_items,
+                        seen_ptr=h.get('seen_ptr'), seen_items=h.get('seen_items'), cols=smp.cols,
+                        ifeat=(h['ifeat_ptr'], h['ifeat_nids']) if entity_aware else None,
+                        ufeat=(h['ufeat_ptr'], h['ufeat_nids']) if entity_aware else None,
+                        type_starts=h.get('type_starts'))
+    assert got.shape == want.shape == (len(ids), 9 if entity_aware else 3)
+    assert np.array_equal(got, want)
+    perm = smp.permutation(2)
+    assert torch.equal(torch.sort(perm).values, torch.arange(n, device=DEV))      # a permutation of the table's rows
+    assert torch.equal(perm, smp.permutation(2)) and not torch.equal(perm, smp.permutation(3))
+
+
+def test_solver_trains_with_device_sampling_and_cuda_graph(tmp_path):
+    """BaseSolver.train_epoch with train_args['device_sampling'] + ['cuda_graph']: the loss goes down."""
+    from graph_recsys_benchmark_b200.solvers import BaseSolver
+    ds = SyntheticHIN_small()
+    torch.manual_seed(3)
+    model = product_model_for(ds, 'gcn')
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, weight_decay=1e-3, capturable=True)
+    solver = BaseSolver(None, {}, {}, {'device': 'cuda', 'batch_size': 512, 'quiet': True, 'device_sampling': True,
+                                       'cuda_graph': True, 'loss_sync_every': 10})
+    _, losses = solver.train_epoch(1, 1, model, opt, ds, max_steps=60)
+    assert len(losses) == 60 and np.isfinite(losses).all()
+    assert np.mean(losses[-10:]) < 0.9 * np.mean(losses[:10])
+
+
+def SyntheticHIN_small():
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+    return SyntheticHIN('tiny', seed=7, sampling_strategy='unseen')

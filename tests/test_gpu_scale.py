@@ -131,3 +131,28 @@ def test_full_size_train_step_is_finite_and_reproducible(big):
     assert outs[0][0] == outs[1][0]
     assert torch.equal(outs[0][1], outs[1][1])                                  # propagation is deterministic
     assert float((outs[0][2] - outs[1][2]).abs().max() / outs[0][2].abs().max()) < 1e-5
+
+
+def test_device_sampler_at_ml25m_shape():
+    """100M-row epoch table, never materialised: a 1M-row batch of the device sampler keeps the
+    reference's invariants (interaction columns, negatives inside the item range and, for 'unseen',
+    outside the user's train set - checked with a sorted-key membership test on the device)."""
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+    from graph_recsys_benchmark_b200.sampling import DeviceBprSampler
+    ds = SyntheticHIN('ml-25m', seed=1234, sampling_strategy='unseen')
+    smp = DeviceBprSampler(ds, 'cuda', seed=9)
+    n = len(smp)
+    assert n == 4 * ds.edge_index_nps['user2item'].shape[1]
+    ids = torch.randint(0, n, (1 << 20,), device='cuda')
+    rows = smp.rows(ids, epoch=1)
+    u2i = smp.tables['u2i']
+    assert torch.equal(rows[:, 0], u2i[0][ids // 4]) and torch.equal(rows[:, 1], u2i[1][ids // 4])
+    lo = ds.type_accs['iid']
+    assert int(rows[:, 2].min()) >= lo and int(rows[:, 2].max()) < lo + ds.num_iids
+    stride = int(ds.num_nodes)
+    keys = torch.sort(u2i[0] * stride + u2i[1]).values
+    probe = rows[:, 0] * stride + rows[:, 2]
+    pos = torch.searchsorted(keys, probe).clamp_(max=keys.numel() - 1)
+    assert not bool((keys[pos] == probe).any())
+    # every unseen item of a user is reachable: one light user's draws cover all of its unseen ids' range ends
+    assert rows[:, 2].unique().numel() > 0.9 * ds.num_iids

@@ -242,3 +242,72 @@ def test_reference_schema_pickle_round_trip(tmp_path):
         d.cf_negative_sampling()
         batches.append(d.get_batch(list(range(50))))
     assert torch.equal(batches[0], batches[1]) and batches[0].shape == (50, 9)
+
+
+# ---- device sampler mirror (oracle/device_sampler.py): pinned generator + the reference's distributions ----------
+def test_philox_known_answer_vectors():
+    """Random123's published known-answer vectors for philox4x32-10 pin the mirror's generator."""
+    from oracle import device_sampler as ods
+    got = [int(v) for v in ods.philox4x32_10(0, 0, 0, 0, 0, 0)]
+    assert got == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = 0xffffffff
+    got = [int(v) for v in ods.philox4x32_10(f, f, f, f, f, f)]
+    assert got == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    got = [int(v) for v in ods.philox4x32_10(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0)]
+    assert got == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def _sampler_tables(ds):
+    from graph_recsys_benchmark_b200.sampling import DeviceBprSampler
+    smp = DeviceBprSampler(ds, 'cpu', seed=77)               # host tables only; rows() needs a GPU
+    h = smp.host
+    kw = dict(num_neg=smp.num_neg, seed=smp.seed, strategy=smp.strategy, user_lo=smp.user_lo, item_lo=smp.item_lo,
+              num_items=smp.num_items, seen_ptr=h.get('seen_ptr'), seen_items=h.get('seen_items'), cols=smp.cols,
+              ifeat=(h['ifeat_ptr'], h['ifeat_nids']) if smp.cols == 9 else None,
+              ufeat=(h['ufeat_ptr'], h['ufeat_nids']) if smp.cols == 9 else None, type_starts=h.get('type_starts'))
+    return smp, h, kw
+
+
+@pytest.mark.parametrize('strategy', ['random', 'unseen'])
+def test_device_sampler_mirror_draws_from_the_reference_distributions(strategy):
+    """Rows of the counter-based sampler: interactions in table order, negatives from the set the reference
+    samples from (random: all items; unseen: items without a train interaction), entity columns as
+    movielens.py:1153-1177, everything a pure function of (seed, epoch, row)."""
+    from oracle import device_sampler as ods
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+    ds = SyntheticHIN('tiny', seed=7, entity_aware=True, sampling_strategy=strategy)
+    smp, h, kw = _sampler_tables(ds)
+    n = len(smp)
+    rows = ods.bpr_rows(np.arange(n), h['u2i'], epoch=3, **kw)
+    assert rows.shape == (n, 9) and n == ds.edge_index_nps['user2item'].shape[1] * 4
+    assert np.array_equal(rows[:, :2], np.repeat(ds.edge_index_nps['user2item'].T, 4, axis=0))
+    lo, hi = ds.type_accs['iid'], ds.type_accs['iid'] + ds.num_iids
+    assert rows[:, 2].min() >= lo and rows[:, 2].max() < hi
+    train = set(map(tuple, ds.edge_index_nps['user2item'].T.tolist()))
+    hits = sum((int(u), int(i)) in train for u, i in rows[:, [0, 2]])
+    if strategy == 'unseen':
+        assert hits == 0
+        pool = {u: set(ds.test_pos_unid_inid_map[u]) | set(ds.neg_unid_inid_map[u]) for u in set(rows[:, 0].tolist())}
+        assert all(int(i) in pool[int(u)] for u, i in rows[:200, [0, 2]])
+    else:
+        assert hits > 0                                         # 'random' may return seen items, as upstream
+    # uniformity over the items (chi-square, loose): 4E draws into num_iids bins
+    if strategy == 'random':
+        cnt = np.bincount(rows[:, 2] - lo, minlength=ds.num_iids)
+        chi2 = float(((cnt - n / ds.num_iids) ** 2 / (n / ds.num_iids)).sum())
+        assert chi2 < ds.num_iids + 6 * np.sqrt(2 * ds.num_iids)
+    # entity columns
+    for col, feats, base in ((3, ds.iid_feat_nids, rows[:, 1] - lo), (6, ds.uid_feat_nids, rows[:, 0] - ds.type_accs['uid'])):
+        for r in range(0, n, 97):
+            fl = list(feats[int(base[r])])
+            pe, ne, m = (int(v) for v in rows[r, col:col + 3])
+            if not fl:
+                assert (pe, ne, m) == (0, 0, 0)
+            else:
+                assert m == 1 and pe in fl
+                et = ds.nid2e_dict[pe][0]
+                assert ds.type_accs[et] <= ne < ds.type_accs[et] + getattr(ds, 'num_' + et + 's')
+    # pure function of (seed, epoch, row): any subset / order gives the same rows; another epoch differs
+    pick = np.array([5, n - 1, 0, 5])
+    assert np.array_equal(ods.bpr_rows(pick, h['u2i'], epoch=3, **kw), rows[pick])
+    assert not np.array_equal(ods.bpr_rows(np.arange(n), h['u2i'], epoch=4, **kw)[:, 2], rows[:, 2])
