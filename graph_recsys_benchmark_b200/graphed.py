@@ -7,7 +7,9 @@ cost: a replay is a single submission (NCCL collectives are captured with it).
 
 Contract (the usual CUDA-graph one):
   * run at least one eager step first, so every lazily built structure (CSR views, kernel attributes,
-    NCCL buffers, optimizer state) exists before the capture;
+    NCCL buffers, optimizer state) exists before the capture - and drop every reference to that step's
+    loss / outputs: tensors that still carry its autograd graph keep AccumulateGrad nodes tied to the
+    default stream alive, and the capture fails with a stream-capture-invalidated error;
   * batches must keep the captured shape - other shapes (the last, short batch of an epoch) go through
     the eager path;
   * do not call ``optimizer.zero_grad()`` between replays: gradients are static tensors owned by the

@@ -165,6 +165,7 @@ class BaseSolver(object):
                 loss.backward()
                 optimizer.step()
                 pending.append(loss.detach())
+                del loss        # a live loss keeps this step's autograd nodes (default stream) alive, which breaks a later capture
             if len(pending) >= sync_every:
                 losses.extend(torch.stack(pending).cpu().tolist())
                 pending = []
