@@ -33,6 +33,9 @@ FLAGS = [
     ('weight_decay', float, 0.001, 'train'), ('early_stopping', int, 20, 'train'),
     ('save_epochs', str, '5,10,15,20,25', 'train'), ('save_every_epoch', int, 26, 'train'),
     ('metapath_test', str, 'true', 'train'), ('loss_sync_every', int, 50, 'train'),
+    # not upstream: whole-step CUDA graph replay, negatives / entity columns drawn on the GPU, processed-HIN pickle
+    ('cuda_graph', str, 'false', 'train'), ('device_sampling', str, 'false', 'train'),
+    ('processed_pickle', str, None, 'data'),
 ]
 MODEL_ONLY_FLAGS = {'PEAGAT': [('num_heads', int, 1, 'model')]}
 
@@ -64,7 +67,7 @@ def argument_dicts(a, model_name):
                         num_negative_samples=a.num_negative_samples, num_core=a.num_core,
                         num_feat_core=a.num_feat_core, cf_loss_type='BPR', type='hete',
                         sampling_strategy=a.sampling_strategy, entity_aware=entity_aware, model=model_name,
-                        synthetic=a.synthetic)
+                        synthetic=a.synthetic, processed_pickle=a.processed_pickle)
     model_args = dict(model_type='Graph', if_use_features=features, emb_dim=a.emb_dim, hidden_size=a.hidden_size,
                       repr_dim=a.repr_dim, dropout=a.dropout, meta_path_steps=_ints(a.meta_path_steps),
                       channel_aggr=a.channel_aggr, entity_aware=entity_aware, entity_aware_coff=a.entity_aware_coff)
@@ -79,7 +82,8 @@ def argument_dicts(a, model_name):
                       lr=a.lr, num_workers=a.num_workers, weights_folder=os.path.join(weights_dir, tag),
                       logger_folder=os.path.join(logger_dir, tag), save_epochs=_ints(a.save_epochs),
                       save_every_epoch=a.save_every_epoch, metapath_test=_flag(a.metapath_test),
-                      loss_sync_every=a.loss_sync_every)
+                      loss_sync_every=a.loss_sync_every, cuda_graph=_flag(a.cuda_graph),
+                      device_sampling=_flag(a.device_sampling))
     for title, d in (('dataset', dataset_args), ('task', model_args), ('train', train_args)):
         print('{} params: {}'.format(title, d))
     return dataset_args, model_args, train_args

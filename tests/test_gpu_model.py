@@ -117,7 +117,8 @@ def test_training_steps_and_metrics_follow_the_oracle(kind, entity_aware):
     assert abs(auc_m[0] - auc_o[0]) < 1e-3 and abs(l_m[0] - l_o[0]) / abs(l_o[0]) < 1e-4
 
 
-def test_experiment_cli_trains_evaluates_checkpoints_and_resumes(tmp_path, monkeypatch, capsys):
+@pytest.mark.parametrize('extra', [[], ['--cuda_graph=true', '--device_sampling=true']])
+def test_experiment_cli_trains_evaluates_checkpoints_and_resumes(tmp_path, monkeypatch, capsys, extra):
     """reference experiments/peagcn_solver_bpr.py flags -> BaseSolver.run(): init eval, 2 epochs,
     checkpoint + global logger written in the reference's layout, resume from latest.pkl."""
     import glob
@@ -129,7 +130,7 @@ def test_experiment_cli_trains_evaluates_checkpoints_and_resumes(tmp_path, monke
     monkeypatch.chdir(tmp_path)
     argv = ['--dataset=Movielens', '--dataset_name=latest-small', '--synthetic=tiny', '--sampling_strategy=unseen',
             '--runs=1', '--epochs=2', '--batch_size=512', '--save_every_epoch=0', '--save_epochs=1',
-            '--metapath_test=false', '--num_workers=0']
+            '--metapath_test=false', '--num_workers=0'] + extra
     pea_cli.run('PEAGCN', models.PEAGCNRecsysModel, argv=argv)
     out = capsys.readouterr().out
     assert 'Initial performance HR@5' in out and 'Run: 1, epoch: 2, HR@5' in out and 'Duration' in out
