@@ -3,7 +3,9 @@
 The PEAGNN step is ~270 kernel launches (aggregations, projections, fusion, scoring, Adam); on one
 GPU the host keeps ahead of the device, but once the propagation is row-sharded over several GPUs each
 rank's kernels shrink and the step becomes launch-bound.  Capturing the step removes the per-launch host
-cost: a replay is a single submission (NCCL collectives are captured with it).
+cost: a replay is a single submission.  Validated on one GPU (tests/test_gpu_model.py, bench.py).  With an
+``allreduce`` hook the NCCL collectives are captured too, but the one 2-GPU trial of round 1 hung, so
+bench.py keeps multi-GPU steps eager until that is understood.
 
 Contract (the usual CUDA-graph one):
   * run at least one eager step first, so every lazily built structure (CSR views, kernel attributes,
