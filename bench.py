@@ -197,7 +197,9 @@ def workload_config(args):
                         % (args.workload, args.model.upper()) if args.workload.startswith('ml-25m') else
                         '%s / PEA%s BPR train step' % (args.workload, args.model.upper()),
             'batch_per_gpu': args.batch, 'optimizer': 'Adam(lr=1e-3, weight_decay=1e-3, fused)',
-            'negatives': 'random', 'l2_between_iterations': 'inputs larger than L2 (CSR + activations > 126 MB)'}
+            'negatives': 'random', 'l2_between_iterations': 'inputs larger than L2 (CSR + activations > 126 MB)',
+            'arithmetic': 'fp32 storage and accumulation everywhere; the 64/16-wide projections run on the tensor '
+                          'cores as a 3-pass TF32 split (hi*hi + hi*lo + lo*hi), fp32-accurate, same 1e-5 parity bound'}
 
 
 # ---------------------------------------------------------------------------------------------
