@@ -559,7 +559,7 @@ extern "C" int peagnn_linear_wgrad(const float* X, int64_t ldx, const float* dY,
     else if (M == 32) rc2 = launch_wgrad_umma<64, 32>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
     else rc2 = launch_wgrad_umma<64, 16>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
     if (rc2) return rc2;
-    wgrad_finalize_v2_kernel<<<(KM + M + 63) / 64, 256, 0, stream>>>(workspace, parts, K, M, w_is_out_in, dW, db);
+    wgrad_finalize_v2_kernel<<<(KM + M + kFinOutputs - 1) / kFinOutputs, 256, 0, stream>>>(workspace, parts, K, M, w_is_out_in, dW, db);
     return check_launch("peagnn_linear_wgrad(umma stage2)");
   }
   if (use_tensor_cores() && ((K == 64 && (M == 64 || M == 32 || M == 16)) || (K == 16 && M == 64))) {
@@ -570,7 +570,7 @@ extern "C" int peagnn_linear_wgrad(const float* X, int64_t ldx, const float* dY,
     else if (M == 32) rc2 = launch_wgrad_tc<64, 32>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
     else rc2 = launch_wgrad_tc<64, 16>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
     if (rc2) return rc2;
-    wgrad_finalize_v2_kernel<<<(KM + M + 63) / 64, 256, 0, stream>>>(workspace, parts, K, M, w_is_out_in, dW, db);
+    wgrad_finalize_v2_kernel<<<(KM + M + kFinOutputs - 1) / kFinOutputs, 256, 0, stream>>>(workspace, parts, K, M, w_is_out_in, dW, db);
     return check_launch("peagnn_linear_wgrad(tc stage2)");
   }
   if (K == 64 && (M == 64 || M == 32 || M == 16)) {   // hot shapes
@@ -580,7 +580,7 @@ extern "C" int peagnn_linear_wgrad(const float* X, int64_t ldx, const float* dY,
     else if (M == 32) rc2 = launch_wgrad_v2<64, 32>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
     else rc2 = launch_wgrad_v2<64, 16>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
     if (rc2) return rc2;
-    wgrad_finalize_v2_kernel<<<(KM + M + 63) / 64, 256, 0, stream>>>(workspace, parts, K, M, w_is_out_in, dW, db);
+    wgrad_finalize_v2_kernel<<<(KM + M + kFinOutputs - 1) / kFinOutputs, 256, 0, stream>>>(workspace, parts, K, M, w_is_out_in, dW, db);
     return check_launch("peagnn_linear_wgrad(v2 stage2)");
   }
   if (K == 0) {

@@ -282,21 +282,29 @@ __global__ void __launch_bounds__(kV2Threads) wgrad_v2_kernel(
   (void)STAGE; (void)FOLD;
 }
 
-// out[idx] = sum over parts, 4 slices of the parts per block folded in order.
+// out[idx] = sum over parts: a CTA owns 16 outputs, 16 threads per output walk interleaved slices of the
+// parts (short dependent chains - this kernel is pure latency), slices folded in a fixed order.
+constexpr int kFinOutputs = 16;
+
 __global__ void __launch_bounds__(256) wgrad_finalize_v2_kernel(const float* __restrict__ partial, int n_parts,
                                                                 int K, int M, int w_is_out_in,
                                                                 float* __restrict__ dW, float* __restrict__ db) {
   __shared__ float red[256];
   const int KM = K * M;
-  const int o = threadIdx.x & 63, s = threadIdx.x >> 6;
-  const int idx = blockIdx.x * 64 + o;
+  const int o = threadIdx.x & (kFinOutputs - 1), s = threadIdx.x / kFinOutputs;
+  constexpr int SLICES = 256 / kFinOutputs;
+  const int idx = blockIdx.x * kFinOutputs + o;
   float v = 0.f;
-  if (idx < KM + M)
-    for (int p = s; p < n_parts; p += 4) v += partial[(size_t)p * (KM + M) + idx];
+  if (idx < KM + M) {
+#pragma unroll 4
+    for (int p = s; p < n_parts; p += SLICES) v += partial[(size_t)p * (KM + M) + idx];
+  }
   red[threadIdx.x] = v;
   __syncthreads();
   if (s == 0 && idx < KM + M) {
-    const float t = (red[o] + red[64 + o]) + (red[128 + o] + red[192 + o]);
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < SLICES; ++q) t += red[q * kFinOutputs + o];
     if (idx < KM) {
       if (dW) {
         const int k = idx / M, m = idx - k * M;
