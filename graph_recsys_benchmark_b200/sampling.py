@@ -55,12 +55,15 @@ class DeviceBprSampler(object):
     def __len__(self):
         return self.E * self.num_neg
 
-    def permutation(self, epoch):
+    def permutation(self, epoch, rank=0, world=1):
         """The epoch's visiting order of the table's rows (the reference shuffles twice: randperm in
-        cf_negative_sampling, then the DataLoader's sampler - one uniform permutation has the same law)."""
+        cf_negative_sampling, then the DataLoader's sampler - one uniform permutation has the same law).
+        Data-parallel runs: every rank draws the same permutation (same seed) and keeps every
+        ``world``-th entry starting at ``rank`` - the ranks' slices partition the epoch."""
         g = torch.Generator(device=self.device)
         g.manual_seed((self.seed * 1000003 + int(epoch)) & 0x7FFFFFFFFFFFFFFF)
-        return torch.randperm(len(self), device=self.device, generator=g)
+        order = torch.randperm(len(self), device=self.device, generator=g)
+        return order if world == 1 else order[rank::world]
 
     def rows(self, row_ids, epoch):
         row_ids = row_ids.to(self.device, dtype=torch.int64).contiguous()

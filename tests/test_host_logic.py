@@ -311,3 +311,14 @@ def test_device_sampler_mirror_draws_from_the_reference_distributions(strategy):
     pick = np.array([5, n - 1, 0, 5])
     assert np.array_equal(ods.bpr_rows(pick, h['u2i'], epoch=3, **kw), rows[pick])
     assert not np.array_equal(ods.bpr_rows(np.arange(n), h['u2i'], epoch=4, **kw)[:, 2], rows[:, 2])
+
+
+def test_device_sampler_rank_slices_partition_the_epoch():
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+    from graph_recsys_benchmark_b200.sampling import DeviceBprSampler
+    smp = DeviceBprSampler(SyntheticHIN('tiny', seed=7), 'cpu', seed=5)
+    whole = smp.permutation(2)
+    parts = [smp.permutation(2, rank=r, world=3) for r in range(3)]
+    assert sorted(torch.cat(parts).tolist()) == list(range(len(smp))) == sorted(whole.tolist())
+    assert all(torch.equal(p, whole[r::3]) for r, p in enumerate(parts))
+    assert not torch.equal(whole, smp.permutation(3))
