@@ -227,7 +227,8 @@ def run_product(args):
     # single GPU: the step is replayed as one CUDA graph.  Multi-GPU stays on eager launches: capturing the
     # NCCL collectives together with the side-stream warm-up hung in the one 2-GPU trial of this round
     # (DESIGN.md section 7), so it is off until that is understood.
-    use_graph = not args.no_cuda_graph and int(os.environ.get('WORLD_SIZE', '1')) == 1
+    use_graph = not args.no_cuda_graph and (int(os.environ.get('WORLD_SIZE', '1')) == 1 or
+                                            bool(os.environ.get('PEAGNN_BENCH_GRAPH_MULTI')))   # opt-in, for debugging
     opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-3, fused=True, capturable=use_graph)
     model.train()
     K, W, B = args.steps, args.warmup, args.batch
