@@ -320,6 +320,7 @@ static int dense_mode() {
     if (e && e[0] == 'f') return 0;
     if (e && e[0] == 'm') return 1;
     if (e && e[0] == 'u') return 2;
+    if (e && e[0] == 'p') return 4;   // "pipe": experimental warp-specialised tcgen05 linear (K = 64 shapes)
     return 3;
   }();
   return mode;
@@ -476,7 +477,11 @@ extern "C" int peagnn_linear(const float* X, int64_t ldx, const float* mask, int
   if (n == 0) return PEAGNN_OK;
   // hot shapes without an input gate: 3xTF32 tensor-core kernels (dense_tc.cuh); PEAGNN_DENSE=ffma keeps
   // the fp32-pipe kernels for A/B timing
-  if (!mask && (dense_mode() == 2 || (dense_mode() == 3 && M == 64)) && (K == 16 || K == 32 || K == 64) &&
+  if (!mask && dense_mode() == 4 && K == 64 && (M == 16 || M == 64)) {
+    if (M == 16) return launch_linear_umma_pipe<64, 16>(X, ldx, n, W, w_is_out_in, bias, relu, accumulate, Y, ldy, out_mask, ldom, stream);
+    return launch_linear_umma_pipe<64, 64>(X, ldx, n, W, w_is_out_in, bias, relu, accumulate, Y, ldy, out_mask, ldom, stream);
+  }
+  if (!mask && (dense_mode() == 2 || (dense_mode() >= 3 && M == 64)) && (K == 16 || K == 32 || K == 64) &&
       (M == 16 || M == 32 || M == 64)) {
 #define PEAGNN_LINUM(K_, N_) \
   return launch_linear_umma<K_, N_>(X, ldx, n, W, w_is_out_in, bias, relu, accumulate, Y, ldy, out_mask, ldom, stream)
@@ -551,7 +556,7 @@ extern "C" int peagnn_linear_wgrad(const float* X, int64_t ldx, const float* dY,
     return check_launch("peagnn_linear_wgrad(memset)");
   }
   if ((dense_mode() == 2 && ((K == 64 && (M == 64 || M == 32 || M == 16)) || (K == 16 && M == 64))) ||
-      (dense_mode() == 3 && K == 64 && M == 64)) {   // default: tcgen05 for the square shape, mma.sync below
+      (dense_mode() >= 3 && K == 64 && M == 64)) {   // default: tcgen05 for the square shape, mma.sync below
     const int64_t rpc = ((n + parts - 1) / parts + kUmWgRows - 1) / kUmWgRows * kUmWgRows;
     int rc2;
     if (K == 16) rc2 = launch_wgrad_umma<16, 64>(X, ldx, dY, ldd, mask, ldm, n, parts, rpc, workspace, stream);
