@@ -684,4 +684,225 @@ static int launch_linear_umma_pipe(const float* X, int64_t ldx, int64_t n, const
   return check_launch("peagnn_linear(umma pipe)");
 }
 
+
+// =================================================================================================
+// EXPERIMENTAL, UNTESTED ON HARDWARE (compiles; PEAGNN_DENSE=ts selects it; written at the end of round 1
+// when no GPU time was left): the TS form of the same GEMM.  The A operand never touches shared memory: every
+// producer thread owns one row of the tile (= one TMEM lane), loads it 32 bytes at a time, splits it and
+// writes A_hi / A_lo straight into tensor memory with tcgen05.st; B (the weight matrix) stays in shared
+// memory.  Tests the hypothesis of profiles/r1_dense_tensor_cores.md that the SS-form TF32 MMAs are bound
+// by the shared-memory operand path.  TMEM columns: [0, 2N) two accumulators, then per stage [A_hi (K) | A_lo (K)].
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int K, int N>
+__global__ void __launch_bounds__(kPipeThreads, 1) linear_umma_ts_kernel(
+    const float* __restrict__ X, int64_t ldx, int64_t n_rows, const float* __restrict__ W, int w_is_out_in,
+    const float* __restrict__ bias, int relu, int accumulate, float* __restrict__ Y, int64_t ldy,
+    const float* __restrict__ out_mask, int64_t ldom) {
+  constexpr int BM = 128;
+  constexpr int KC = K / 4, KS = K / 8;
+  constexpr int KPW = KS / 2;                              // k-steps per producer warp (two warps share a lane quarter)
+  constexpr uint32_t B_SBO = 128, B_LBO = (N / 8) * 128;
+  constexpr int B_BYTES = N * K * 4;
+  constexpr uint32_t A_COL0 = 2 * N;                       // first TMEM column of the A stages
+  constexpr uint32_t TMEM_NEED = 2 * N + 4 * K;
+  constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
+  constexpr int SP = N + 4;
+  static_assert(K % 16 == 0 && N % 16 == 0 && N <= 64 && TMEM_NEED <= 512, "unsupported shape");
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  extern __shared__ __align__(128) uint8_t umma_smem[];
+  uint8_t* sBh = umma_smem;
+  uint8_t* sBl = sBh + B_BYTES;
+  float* sOut = reinterpret_cast<float*>(sBl + B_BYTES);   // [4 warps][32][SP]
+  __shared__ __align__(8) uint64_t bars[8];                // full[2] empty[2] acc_full[2] acc_empty[2]
+  __shared__ uint32_t tmem_base_slot;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bars[0 + s]), 32 * kPipeProducerWarps);
+      mbar_init(smem_u32(&bars[2 + s]), 1);
+      mbar_init(smem_u32(&bars[4 + s]), 1);
+      mbar_init(smem_u32(&bars[6 + s]), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int idx = threadIdx.x; idx < N * KC; idx += kPipeThreads) {
+    const int j = idx / N, n = idx - j * N;
+    float w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      w[e] = w_is_out_in ? __ldg(W + (size_t)n * K + 4 * j + e) : __ldg(W + (size_t)(4 * j + e) * N + n);
+    uint4 hi, lo;
+    split_tf32(w[0], hi.x, lo.x); split_tf32(w[1], hi.y, lo.y);
+    split_tf32(w[2], hi.z, lo.z); split_tf32(w[3], hi.w, lo.w);
+    const uint32_t off = (uint32_t)(j * (N / 8) + (n >> 3)) * 128u + (uint32_t)(n & 7) * 16u;
+    *reinterpret_cast<uint4*>(sBh + off) = hi;
+    *reinterpret_cast<uint4*>(sBl + off) = lo;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
+  const uint32_t afull0 = smem_u32(&bars[4]), aempty0 = smem_u32(&bars[6]);
+  const int64_t n_tiles = (n_rows + BM - 1) / BM;
+  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp < kPipeProducerWarps) {
+    // ---------------------------------------------------------------- producers: one row (= TMEM lane) per thread
+    const int q = warp & 3, h = warp >> 2;
+    float4 pre0[2 * KPW], pre1[2 * KPW];
+    auto fetch = [&](int64_t i, float4 (&pre)[2 * KPW]) {
+      const int64_t row = (blockIdx.x + i * gridDim.x) * BM + 32 * q + lane;
+      const bool ok = i < my_tiles && row < n_rows;
+#pragma unroll
+      for (int j = 0; j < 2 * KPW; ++j)
+        pre[j] = ok ? ldg4(X + row * ldx + 8 * (h * KPW) + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto produce = [&](int64_t i, float4 (&pre)[2 * KPW]) {
+      const int s = (int)(i & 1);
+      mbar_wait(empty0 + 8 * s, (uint32_t)(((i >> 1) & 1) ^ 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = tmem_base + ((uint32_t)(32 * q) << 16) + A_COL0 + (uint32_t)(s * 2 * K) + 8u * (uint32_t)(h * KPW);
+#pragma unroll
+      for (int j = 0; j < KPW; ++j) {
+        uint32_t hi[8], lo[8];
+        split_tf32_fast(pre[2 * j].x, hi[0], lo[0]); split_tf32_fast(pre[2 * j].y, hi[1], lo[1]);
+        split_tf32_fast(pre[2 * j].z, hi[2], lo[2]); split_tf32_fast(pre[2 * j].w, hi[3], lo[3]);
+        split_tf32_fast(pre[2 * j + 1].x, hi[4], lo[4]); split_tf32_fast(pre[2 * j + 1].y, hi[5], lo[5]);
+        split_tf32_fast(pre[2 * j + 1].z, hi[6], lo[6]); split_tf32_fast(pre[2 * j + 1].w, hi[7], lo[7]);
+        tmem_st8(a_hi + 8 * j, hi);
+        tmem_st8(a_hi + K + 8 * j, lo);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(full0 + 8 * s);
+      fetch(i + 2, pre);
+    };
+    fetch(0, pre0);
+    fetch(1, pre1);
+    for (int64_t i = 0; i < my_tiles; i += 2) {
+      produce(i, pre0);
+      if (i + 1 < my_tiles) produce(i + 1, pre1);
+    }
+  } else if (warp == kPipeProducerWarps + 4) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t bH = smem_u32(sBh), bL = smem_u32(sBl);
+      for (int64_t i = 0; i < my_tiles; ++i) {
+        const int s = (int)(i & 1);
+        const uint32_t par = (uint32_t)((i >> 1) & 1);
+        mbar_wait(full0 + 8 * s, par);
+        mbar_wait(aempty0 + 8 * s, par ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = tmem_base + A_COL0 + (uint32_t)(s * 2 * K), a_lo = a_hi + K;
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t a0 = term == 0 ? a_lo : a_hi;
+          const uint32_t b0 = term == 1 ? bL : bH;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks)
+            umma_tf32_ts(tmem_base + s * N, a0 + 8 * ks, umma_desc(b0 + ks * 2 * B_LBO, B_LBO, B_SBO), IDESC,
+                         (term | ks) != 0);
+        }
+        umma_commit(empty0 + 8 * s);
+        umma_commit(afull0 + 8 * s);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (as in linear_umma_pipe_kernel)
+    const int q = warp - kPipeProducerWarps;
+    float* stage = sOut + q * (32 * SP);
+    constexpr int C4 = N / 4;
+    constexpr int RPI = 32 / C4;
+    const int c = 4 * (lane % C4);
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) bv = ldg4(bias + c);
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      const int s = (int)(i & 1);
+      mbar_wait(afull0 + 8 * s, (uint32_t)((i >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      __syncwarp();
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(s * N);
+#pragma unroll
+      for (int u = 0; u < N / 8; ++u) {
+        float v[8];
+        tmem_ld8(taddr + 8 * u, v);
+        st4(stage + lane * SP + 8 * u, make_float4(v[0], v[1], v[2], v[3]));
+        st4(stage + lane * SP + 8 * u + 4, make_float4(v[4], v[5], v[6], v[7]));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(aempty0 + 8 * s);
+      __syncwarp();
+      const int64_t tile = blockIdx.x + i * gridDim.x;
+#pragma unroll
+      for (int it = 0; it < 32 / RPI; ++it) {
+        const int r = it * RPI + lane / C4;
+        const int64_t row = tile * BM + 32 * q + r;
+        if (row < n_rows) {
+          float4 o = *reinterpret_cast<const float4*>(stage + r * SP + c);
+          o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+          float* yp = Y + row * ldy + c;
+          if (accumulate) {
+            const float4 p = *reinterpret_cast<const float4*>(yp);
+            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+          }
+          if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (out_mask) {
+            const float4 g = ldg4(out_mask + row * ldom + c);
+            o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
+          }
+          st4(yp, o);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+template <int K, int N>
+static int launch_linear_umma_ts(const float* X, int64_t ldx, int64_t n, const float* W, int w_is_out_in,
+                                 const float* bias, int relu, int accumulate, float* Y, int64_t ldy,
+                                 const float* out_mask, int64_t ldom, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)2 * (N * K * 4) + (size_t)4 * 32 * (N + 4) * 4 + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(linear_umma_ts_kernel<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  const int64_t tiles = (n + 127) / 128;
+  const int blocks = (int)imin64(tiles, (int64_t)kNumSMs);
+  linear_umma_ts_kernel<K, N><<<blocks, kPipeThreads, smem, stream>>>(X, ldx, n, W, w_is_out_in, bias, relu, accumulate,
+                                                                    Y, ldy, out_mask, ldom);
+  return check_launch("peagnn_linear(umma ts)");
+}
+
 }  // namespace peagnn
