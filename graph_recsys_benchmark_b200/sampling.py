@@ -66,6 +66,9 @@ class DeviceBprSampler(object):
         return order if world == 1 else order[rank::world]
 
     def rows(self, row_ids, epoch):
+        if self.device.type != 'cuda':
+            raise RuntimeError('DeviceBprSampler.rows runs peagnn_bpr_rows on a CUDA device; there is no CPU path '
+                               '(a CPU sampler object only holds the host tables)')
         row_ids = row_ids.to(self.device, dtype=torch.int64).contiguous()
         out = torch.empty(row_ids.numel(), self.cols, dtype=torch.int64, device=self.device)
         t = self.tables

@@ -322,3 +322,11 @@ def test_device_sampler_rank_slices_partition_the_epoch():
     assert sorted(torch.cat(parts).tolist()) == list(range(len(smp))) == sorted(whole.tolist())
     assert all(torch.equal(p, whole[r::3]) for r, p in enumerate(parts))
     assert not torch.equal(whole, smp.permutation(3))
+
+
+def test_device_sampler_has_no_cpu_path():
+    from graph_recsys_benchmark_b200.datasets import SyntheticHIN
+    from graph_recsys_benchmark_b200.sampling import DeviceBprSampler
+    smp = DeviceBprSampler(SyntheticHIN('tiny', seed=7), 'cpu', seed=5)
+    with pytest.raises(RuntimeError):
+        smp.rows(torch.arange(4), epoch=0)
