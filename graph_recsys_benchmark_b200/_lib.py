@@ -24,6 +24,7 @@ class CsrView(C.Structure):
         ('partial', C.c_void_p),
         ('nnz', C.c_int64),
         ('explicit_self_loops', C.c_int32), ('reserved', C.c_int32),
+        ('active_rows', C.c_void_p), ('active_cols', C.c_void_p),
     ]
 
 
@@ -41,6 +42,8 @@ SIGNATURES = {
     'peagnn_degree_scale': (_INT, [_P, _I32, _F, _F, _INT, _P, _P]),
     'peagnn_partial_floats': (_SZ, [_I32, _I32, _I32]),
     'peagnn_spmm': (_INT, [_G, _P, _I64, _I32, _P, _I64, _P, _P, _INT, _P, _INT, _INT, _P]),
+    'peagnn_spmm_filtered': (_INT, [_G, _P, _I64, _I32, _P, _I64, _P, _P, _INT, _P, _INT, _INT, _P, _P, _P]),
+    'peagnn_mark_rows': (_INT, [_P, _I64, _I32, _I32, _P, _P]),
     'peagnn_gat_rowmax': (_INT, [_G, _P, _P, _I32, _F, _P, _P]),
     'peagnn_gat_aggregate': (_INT, [_G, _P, _I64, _I32, _I32, _P, _P, _F, _P, _P, _P, _I64, _P, _INT, _P]),
     'peagnn_gat_backward_dst': (_INT, [_G, _P, _I64, _I32, _I32, _P, _P, _F, _P, _P, _P, _I64, _P, _P, _I64,
@@ -60,9 +63,12 @@ SIGNATURES = {
     'peagnn_bpr_workspace_floats': (_SZ, [_I64, _I32]),
     'peagnn_bpr_loss': (_INT, [_P, _I64, _I32, _P, _I32, _I64, _P, _P, _P, _P, _P, _INT, _P, _I64, _P, _P, _P, _P,
                                _P, _SZ, _P]),
+    'peagnn_entity_workspace_floats': (_SZ, [_I64, _I32, _INT]),
     'peagnn_entity_reg': (_INT, [_P, _I64, _I32, _P, _I64, _F, _P, _INT, _P, _I64, _P, _SZ, _P]),
     'peagnn_eval_rank': (_INT, [_P, _I64, _I32, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     'peagnn_column_mean': (_INT, [_P, _I64, _I64, _I32, _P, _P, _SZ, _P]),
+    'peagnn_probe_out_floats': (_SZ, []),
+    'peagnn_probe_gather': (_INT, [_P, _I64, _I32, _P, _I64, _P, _P]),
     'peagnn_bpr_rows': (_INT, [_P, _I64, _P, _I64, _I32, _U64, _U64, _I32, _I64, _I64, _I64, _P, _P, _I32,
                                _P, _P, _P, _P, _P, _I32, _P, _P]),
 }
@@ -94,23 +100,27 @@ def last_error():
     return load().peagnn_last_error().decode('utf-8', 'replace')
 
 
-profile = None      # when a list: every call appends (entry point, start event, end event)
+profile = None      # when a list: every call appends (tag or entry point, algorithmic bytes, start event, end event)
 _fns = {}           # entry point name -> bound ctypes function
 
 
-def call(name, *args):
-    """Invoke an int-returning entry point; raise on a non-zero code."""
+def call(name, *args, tag=None, nbytes=0):
+    """Invoke an int-returning entry point; raise on a non-zero code.  With ``profile`` set, the launch is
+    bracketed by CUDA events on the current stream - ``external`` ones while a CUDA graph is being captured,
+    so they become event-record nodes that every replay re-records and ``elapsed_time`` can read."""
     global launch_count
     fn = _fns.get(name)
     if fn is None:
         fn = _fns[name] = getattr(load(), name)
     if profile is not None:
         import torch
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ext = torch.cuda.is_current_stream_capturing()
+        e0 = torch.cuda.Event(enable_timing=True, external=ext)
+        e1 = torch.cuda.Event(enable_timing=True, external=ext)
         e0.record()
         rc = fn(*args)
         e1.record()
-        profile.append((name, e0, e1))
+        profile.append((tag or name, nbytes, e0, e1))
     else:
         rc = fn(*args)
     launch_count += 1

@@ -3,6 +3,7 @@
 // These kernels touch only B <= a few thousand rows: they are latency-bound, so the design goal
 // is few launches and no host synchronisation, not bandwidth.
 #include "common.cuh"
+#include "scatter_sorted.cuh"
 
 namespace peagnn {
 
@@ -92,9 +93,9 @@ __global__ void __launch_bounds__(128) bpr_kernel(const float* __restrict__ repr
                                                   const int64_t* __restrict__ batch, int cols, int64_t B,
                                                   const float* w1, const float* b1, const float* w2, const float* b2,
                                                   float* __restrict__ loss_terms, int need_grad,
-                                                  float* __restrict__ d_repr, int64_t lddr, float* __restrict__ cat,
-                                                  float* __restrict__ dh, float* __restrict__ hid,
-                                                  float* __restrict__ g4) {
+                                                  int32_t* __restrict__ gkeys, float* __restrict__ grows,
+                                                  float* __restrict__ cat, float* __restrict__ dh,
+                                                  float* __restrict__ hid, float* __restrict__ g4) {
   __shared__ FcSmem<D> s;
   load_fc<D>(s, w1, b1, w2, b2);
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,11 +111,10 @@ __global__ void __launch_bounds__(128) bpr_kernel(const float* __restrict__ repr
   load_row<D>(repr, ldr, nid, itn);
   const float sn = item_score<D>(s, hu, itn, pre_n);
   const float z = sp - sn;
-  const float sig = 1.f / (1.f + expf(-z));
-  loss_terms[b] = -logf(sig);
+  loss_terms[b] = neg_log_sigmoid(z);
   if (!need_grad) return;
 
-  const float g = sig - 1.f;  // d(-log sigmoid(z))/dz ; d/dsp = g, d/dsn = -g
+  const float g = neg_log_sigmoid_grad(z);  // d(-log sigmoid(z))/dz ; d/dsp = g, d/dsn = -g
   float du[D], dp[D], dn[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) du[k] = dp[k] = dn[k] = 0.f;
@@ -143,11 +143,14 @@ __global__ void __launch_bounds__(128) bpr_kernel(const float* __restrict__ repr
   }
   g4[b * 4] = g; g4[b * 4 + 1] = 0.f; g4[b * 4 + 2] = 0.f; g4[b * 4 + 3] = 0.f;
   g4[(B + b) * 4] = -g; g4[(B + b) * 4 + 1] = 0.f; g4[(B + b) * 4 + 2] = 0.f; g4[(B + b) * 4 + 3] = 0.f;
+  // row gradients go to slots b (user), B + b (positive item), 2B + b (negative item) of a [3B, D] scratch;
+  // scatter_rows_sorted() adds them into d_repr in a fixed order (no float atomics: bit-reproducible)
+  gkeys[b] = (int32_t)uid; gkeys[B + b] = (int32_t)pid; gkeys[2 * B + b] = (int32_t)nid;
 #pragma unroll
   for (int c = 0; c < D / 4; ++c) {
-    atomicAdd(reinterpret_cast<float4*>(d_repr + uid * lddr + 4 * c), make_float4(du[4 * c], du[4 * c + 1], du[4 * c + 2], du[4 * c + 3]));
-    atomicAdd(reinterpret_cast<float4*>(d_repr + pid * lddr + 4 * c), make_float4(dp[4 * c], dp[4 * c + 1], dp[4 * c + 2], dp[4 * c + 3]));
-    atomicAdd(reinterpret_cast<float4*>(d_repr + nid * lddr + 4 * c), make_float4(dn[4 * c], dn[4 * c + 1], dn[4 * c + 2], dn[4 * c + 3]));
+    st4(grows + (size_t)b * D + 4 * c, make_float4(du[4 * c], du[4 * c + 1], du[4 * c + 2], du[4 * c + 3]));
+    st4(grows + (size_t)(B + b) * D + 4 * c, make_float4(dp[4 * c], dp[4 * c + 1], dp[4 * c + 2], dp[4 * c + 3]));
+    st4(grows + (size_t)(2 * B + b) * D + 4 * c, make_float4(dn[4 * c], dn[4 * c + 1], dn[4 * c + 2], dn[4 * c + 3]));
   }
 }
 
@@ -177,7 +180,7 @@ __global__ void copy_row0_kernel(const float* __restrict__ src, int n, float* __
 __global__ void __launch_bounds__(256) entity_kernel(const float* __restrict__ x, int64_t ldx, int emb,
                                                      const int64_t* __restrict__ batch, int64_t B, float coff,
                                                      float* __restrict__ terms, int need_grad,
-                                                     float* __restrict__ dx, int64_t lddx) {
+                                                     int32_t* __restrict__ gkeys, float* __restrict__ grows) {
   const int lane = threadIdx.x & 31;
   const int64_t b = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
   if (b >= B) return;
@@ -206,17 +209,24 @@ __global__ void __launch_bounds__(256) entity_kernel(const float* __restrict__ x
       sn += __shfl_xor_sync(0xffffffffu, sn, o);
     }
     const float z = (sp - sn) * mask;
-    const float sig = 1.f / (1.f + expf(-z));
-    total += -logf(sig);
-    if (need_grad && on && mask != 0.f) {
-      const float gz = (sig - 1.f) * mask * coff * 2.f;   // d/d(sp) = gz/2 * 2 (from the square)
-      // d anchor = gz * (dp - dn) ; d epos = -gz * dp ; d eneg = +gz * dn
-      atomicAdd(reinterpret_cast<float4*>(dx + anchor * lddx + 4 * lane),
-                make_float4(gz * (dp.x - dn.x), gz * (dp.y - dn.y), gz * (dp.z - dn.z), gz * (dp.w - dn.w)));
-      atomicAdd(reinterpret_cast<float4*>(dx + epos * lddx + 4 * lane),
-                make_float4(-gz * dp.x, -gz * dp.y, -gz * dp.z, -gz * dp.w));
-      atomicAdd(reinterpret_cast<float4*>(dx + eneg * lddx + 4 * lane),
-                make_float4(gz * dn.x, gz * dn.y, gz * dn.z, gz * dn.w));
+    total += neg_log_sigmoid(z);
+    if (need_grad) {
+      // slots (side, b, {anchor, e+, e-}) of a [6B, emb] scratch, summed into dx in a fixed order afterwards
+      const int64_t slot = ((int64_t)side * B + b) * 3;
+      const bool live = mask != 0.f;
+      if (lane == 0) {
+        gkeys[slot] = live ? (int32_t)anchor : kScatterSkip;
+        gkeys[slot + 1] = live ? (int32_t)epos : kScatterSkip;
+        gkeys[slot + 2] = live ? (int32_t)eneg : kScatterSkip;
+      }
+      if (on && live) {
+        const float gz = neg_log_sigmoid_grad(z) * mask * coff * 2.f;   // d/d(sp) = gz/2 * 2 (from the square)
+        // d anchor = gz * (dp - dn) ; d epos = -gz * dp ; d eneg = +gz * dn
+        st4(grows + (size_t)slot * emb + 4 * lane,
+            make_float4(gz * (dp.x - dn.x), gz * (dp.y - dn.y), gz * (dp.z - dn.z), gz * (dp.w - dn.w)));
+        st4(grows + (size_t)(slot + 1) * emb + 4 * lane, make_float4(-gz * dp.x, -gz * dp.y, -gz * dp.z, -gz * dp.w));
+        st4(grows + (size_t)(slot + 2) * emb + 4 * lane, make_float4(gz * dn.x, gz * dn.y, gz * dn.z, gz * dn.w));
+      }
     }
   }
   if (lane == 0) terms[b] = total;
@@ -242,15 +252,19 @@ static int run_bpr(const float* repr, int64_t ldr, const int64_t* batch, int col
   float* hid = ws + off; off += (size_t)2 * B * D;
   float* g4 = ws + off; off += (size_t)2 * B * 4;
   float* tmp = ws + off; off += 4 * D + 4;   // [4, D] result of the fc2 weight gradient + db scratch
-  float* wg = ws + off;
+  float* grows = ws + off; off += (size_t)3 * B * D;
+  int32_t* gkeys = reinterpret_cast<int32_t*>(ws + off); off += ((size_t)3 * B + 3) / 4 * 4;
+  float* wg = ws + off;       // the weight-gradient scratch and the scatter's sort scratch take turns here
   const size_t wg_floats = ws_floats - off;
   bpr_kernel<D><<<(unsigned)((B + 127) / 128), 128, 0, stream>>>(repr, ldr, batch, cols, B, w1, b1, w2, b2, terms,
-                                                               need_grad, d_repr, lddr, cat, dh, hid, g4);
+                                                               need_grad, gkeys, grows, cat, dh, hid, g4);
   int rc = check_launch("peagnn_bpr_loss");
   if (rc) return rc;
   sum_terms_kernel<<<1, 1024, 0, stream>>>(terms, B, 1.f, 0, loss);
   rc = check_launch("peagnn_bpr_loss(sum)");
   if (rc || !need_grad) return rc;
+  rc = scatter_rows_sorted(gkeys, grows, D, 3 * B, d_repr, lddr, wg, stream, "peagnn_bpr_loss(scatter)");
+  if (rc) return rc;
   // d fc1.weight [D, 2D] = dh^T @ cat ; d fc1.bias = colsum(dh)
   rc = peagnn_linear_wgrad(cat, 2 * D, dh, D, nullptr, 0, 2 * B, 2 * D, D, /*out_in=*/1, d_w1, d_b1, wg, wg_floats, stream);
   if (rc) return rc;
@@ -288,10 +302,14 @@ extern "C" int peagnn_predict(const float* repr, int64_t ldr, int32_t D, const i
 }
 
 extern "C" size_t peagnn_bpr_workspace_floats(int64_t B, int32_t D) {
-  const size_t fixed = ((size_t)B + 3) / 4 * 4 + (size_t)2 * B * (2 * D + D + D + 4) + 4 * D + 4;
+  const size_t fixed = ((size_t)B + 3) / 4 * 4 + (size_t)2 * B * (2 * D + D + D + 4) + 4 * D + 4 +
+                       (size_t)3 * B * D + ((size_t)3 * B + 3) / 4 * 4;
   const size_t w1 = peagnn_wgrad_workspace_floats(2 * B, 2 * D, D);
   const size_t w2 = peagnn_wgrad_workspace_floats(2 * B, D, 4);
-  return fixed + (w1 > w2 ? w1 : w2) + 64;
+  const size_t sc = (scatter_scratch_bytes(3 * B) + 3) / 4;
+  size_t turn = w1 > w2 ? w1 : w2;
+  if (sc > turn) turn = sc;
+  return fixed + turn + 64;
 }
 
 extern "C" int peagnn_bpr_loss(const float* repr, int64_t ldr, int32_t D, const int64_t* batch,
@@ -317,6 +335,12 @@ extern "C" int peagnn_bpr_loss(const float* repr, int64_t ldr, int32_t D, const 
 #undef CASE
 }
 
+extern "C" size_t peagnn_entity_workspace_floats(int64_t B, int32_t emb, int need_grad) {
+  const size_t terms = ((size_t)B + 3) / 4 * 4;
+  if (!need_grad) return terms;
+  return terms + (size_t)6 * B * emb + ((size_t)6 * B + 3) / 4 * 4 + (scatter_scratch_bytes(6 * B) + 3) / 4 + 64;
+}
+
 extern "C" int peagnn_entity_reg(const float* x, int64_t ldx, int32_t emb, const int64_t* batch, int64_t B,
                                  float coff, float* loss, int need_grad, float* dx, int64_t lddx,
                                  float* workspace, size_t workspace_floats, peagnn_stream_t stream_) {
@@ -324,10 +348,19 @@ extern "C" int peagnn_entity_reg(const float* x, int64_t ldx, int32_t emb, const
   PEAGNN_REQUIRE(x && batch && loss && workspace && emb > 0 && emb % 4 == 0 && emb <= 128 && ldx % 4 == 0 && aligned16(x) && B > 0,
                  "peagnn_entity_reg: emb must be a multiple of 4, <= 128");
   PEAGNN_REQUIRE(!need_grad || (dx && lddx % 4 == 0 && aligned16(dx)), "peagnn_entity_reg: dx missing");
-  PEAGNN_REQUIRE(workspace_floats >= (size_t)B, "peagnn_entity_reg: workspace %zu < %lld floats", workspace_floats, (long long)B);
-  entity_kernel<<<(unsigned)((B * 32 + 255) / 256), 256, 0, stream>>>(x, ldx, emb, batch, B, coff, workspace, need_grad, dx, lddx);
+  const size_t need = peagnn_entity_workspace_floats(B, emb, need_grad);
+  PEAGNN_REQUIRE(workspace_floats >= need && aligned16(workspace), "peagnn_entity_reg: workspace %zu < %zu floats",
+                 workspace_floats, need);
+  const size_t terms_f = ((size_t)B + 3) / 4 * 4;
+  float* grows = workspace + terms_f;
+  int32_t* gkeys = reinterpret_cast<int32_t*>(grows + (size_t)6 * B * emb);
+  float* scratch = reinterpret_cast<float*>(gkeys) + ((size_t)6 * B + 3) / 4 * 4;
+  entity_kernel<<<(unsigned)((B * 32 + 255) / 256), 256, 0, stream>>>(x, ldx, emb, batch, B, coff, workspace, need_grad,
+                                                                     gkeys, grows);
   int rc = check_launch("peagnn_entity_reg");
   if (rc) return rc;
   sum_terms_kernel<<<1, 1024, 0, stream>>>(workspace, B, coff, 1, loss);
-  return check_launch("peagnn_entity_reg(sum)");
+  rc = check_launch("peagnn_entity_reg(sum)");
+  if (rc || !need_grad) return rc;
+  return scatter_rows_sorted(gkeys, grows, emb, 6 * B, dx, lddx, scratch, stream, "peagnn_entity_reg(scatter)");
 }

@@ -50,11 +50,15 @@ __device__ __forceinline__ size_t row_off(int c, unsigned ld) {
 
 __device__ __forceinline__ float leaky(float s, float slope) { return s > 0.f ? s : slope * s; }
 
-// -log(sigmoid(z)) evaluated the way the reference does it (sigmoid().log(), models/base.py:48):
-// no logsigmoid stabilisation, so a very negative z overflows to +inf exactly as upstream.
-__device__ __forceinline__ float neg_log_sigmoid_ref(float z) {
-  float s = 1.f / (1.f + expf(-z));
-  return -logf(s);
+// -log(sigmoid(z)) = softplus(-z), evaluated without overflow.  The reference spells it
+// sigmoid().log() (models/base.py:48), which torch keeps finite down to z ~ -103 (denormal sigmoid);
+// a literal 1/(1+expf(-z)) already overflows at z < -88.7 and would turn one outlier triple into an
+// infinite summed loss.  This form agrees with the reference to fp32 rounding wherever the reference is
+// finite and stays finite beyond.
+__device__ __forceinline__ float neg_log_sigmoid(float z) {
+  return fmaxf(-z, 0.f) + log1pf(expf(-fabsf(z)));
 }
+// d/dz of the above = sigmoid(z) - 1 = -1 / (1 + e^z); expf(z) -> inf gives -0, -> 0 gives -1
+__device__ __forceinline__ float neg_log_sigmoid_grad(float z) { return -1.f / (1.f + expf(z)); }
 
 }  // namespace peagnn

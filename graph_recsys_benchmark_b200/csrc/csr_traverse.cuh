@@ -60,6 +60,49 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
+__device__ __forceinline__ bool bit_set(const uint32_t* __restrict__ bm, int id) {
+  return (__ldg(bm + (id >> 5)) >> (id & 31)) & 1u;
+}
+
+// Filtered form of process_batches: edges whose gathered node is inactive are dropped before they reach the
+// slots.  A batch of 32 edges costs one coalesced index load, one bitmap probe and a ballot when nothing in
+// it is active (the common case when the filter is a training batch); the survivors keep their order.
+template <class Op, int G>
+__device__ __forceinline__ void process_batches_filtered(Op& op, const int32_t* __restrict__ col,
+                                                         const uint32_t* __restrict__ active, int first, int end,
+                                                         int step, float* acc, int lane, int safe_row) {
+  constexpr int EPW = 32 / G;
+  const int gl = lane % G;
+  const int slot = lane / G;
+  for (int base = first; base < end; base += step) {
+    const int e = base + lane;
+    int c = safe_row;
+    bool on = false;
+    if (e < end) {
+      c = __ldg(col + e);
+      on = bit_set(active, c);
+    }
+    const unsigned act = __ballot_sync(kFull, on);
+    if (act == 0u) continue;
+    Edge cur;
+    if (on) {
+      cur = op.load_edge(e, c);
+    } else {
+      cur.c = safe_row; cur.w = 0.f; cur.w2 = 0.f;
+    }
+    const int n_act = __popc(act);
+    for (int s = 0; s * EPW < n_act; ++s) {
+      const int k = s * EPW + slot;
+      const bool valid = k < n_act;
+      const int src = (int)__fns(act, 0, valid ? k + 1 : 1);
+      const int cc = __shfl_sync(kFull, cur.c, src);
+      const float w = __shfl_sync(kFull, cur.w, src);
+      const float w2 = Op::kUseW2 ? __shfl_sync(kFull, cur.w2, src) : 0.f;
+      op.apply(acc, base + src, cc, w, w2, gl, valid);
+    }
+  }
+}
+
 // Process the 32-edge batches first, first + step, ... < end of one row.
 template <class Op, int G>
 __device__ __forceinline__ void process_batches(Op& op, const int32_t* __restrict__ col, int first,
@@ -122,7 +165,7 @@ __device__ __forceinline__ void fold_slots(float* acc) {
 }
 
 // Launch 1 (only when the view has heavy rows): one CTA per (chunk, head).
-template <class Op, int G>
+template <class Op, int G, bool FILT = false>
 __global__ void __launch_bounds__(kCtaThreads) csr_chunk_kernel(const peagnn_csr_t g, const Op op_in) {
   __shared__ float sm[kWarpsPerCta * G * Op::NV];
   Op op = op_in;
@@ -133,12 +176,17 @@ __global__ void __launch_bounds__(kCtaThreads) csr_chunk_kernel(const peagnn_csr
   const int warp = threadIdx.x >> 5;
   const int gl = lane % G;
   const int i = g.chunk_row[chunk];
+  if (FILT && g.active_rows && !bit_set(g.active_rows, i)) return;     // nobody folds this row's partials
   const int cb = g.chunk_begin[chunk], ce = g.chunk_end[chunk];
   float acc[Op::NV];
 #pragma unroll
   for (int v = 0; v < Op::NV; ++v) acc[v] = identity<Op>();
   op.row_begin(i, h, gl);
-  process_batches<Op, G>(op, g.col, cb + warp * 32, ce, kWarpsPerCta * 32, acc, lane, g.row_offset + i);
+  if (FILT && g.active_cols)
+    process_batches_filtered<Op, G>(op, g.col, g.active_cols, cb + warp * 32, ce, kWarpsPerCta * 32, acc, lane,
+                                    g.row_offset + i);
+  else
+    process_batches<Op, G>(op, g.col, cb + warp * 32, ce, kWarpsPerCta * 32, acc, lane, g.row_offset + i);
   fold_slots<Op, G>(acc);
   if (lane < G) {
 #pragma unroll
@@ -156,7 +204,7 @@ __global__ void __launch_bounds__(kCtaThreads) csr_chunk_kernel(const peagnn_csr
 
 // Launch 2: the first blocks fold the heavy rows' chunk partials, the rest take kRowsPerWarp light
 // rows per warp.
-template <class Op, int G, int RPW>
+template <class Op, int G, int RPW, bool FILT = false>
 __global__ void __launch_bounds__(kCtaThreads) csr_rows_kernel(const peagnn_csr_t g, const Op op_in) {
   Op op = op_in;
   const int heads = op.heads;
@@ -176,6 +224,7 @@ __global__ void __launch_bounds__(kCtaThreads) csr_rows_kernel(const peagnn_csr_
     const int hi = (int)(hl / heads);
     const int h = (int)(hl - (long long)hi * heads);
     const int i = g.heavy_rows[hi];
+    if (FILT && g.active_rows && !bit_set(g.active_rows, i)) return;
     op.row_begin(i, h, gl);
     const int c0 = g.heavy_chunk_ptr[hi], c1 = g.heavy_chunk_ptr[hi + 1];
     for (int ch = c0; ch < c1; ++ch) {
@@ -195,7 +244,8 @@ __global__ void __launch_bounds__(kCtaThreads) csr_rows_kernel(const peagnn_csr_
   const long long lr0 = (((long long)blockIdx.x - heavy_blocks) * kWarpsPerCta + warp) * RPW;
   if (lr0 >= total) return;
   const long long my_lr = lr0 + lane;
-  const bool mine = lane < RPW && my_lr < total;
+  bool mine = lane < RPW && my_lr < total;
+  if (FILT && g.active_rows && mine) mine = bit_set(g.active_rows, (int)(my_lr / heads));
   int start_l = 0, end_l = 0;
   if (mine) {
     const int i_l = (int)(my_lr / heads);
@@ -233,20 +283,23 @@ __global__ void __launch_bounds__(kCtaThreads) csr_rows_kernel(const peagnn_csr_
 #pragma unroll
     for (int v = 0; v < Op::NV; ++v) acc[v] = identity<Op>();
     op.row_begin(i, h, gl);
-    process_batches<Op, G>(op, g.col, start, end, 32, acc, lane, g.row_offset + i);
+    if (FILT && g.active_cols)
+      process_batches_filtered<Op, G>(op, g.col, g.active_cols, start, end, 32, acc, lane, g.row_offset + i);
+    else
+      process_batches<Op, G>(op, g.col, start, end, 32, acc, lane, g.row_offset + i);
     fold_slots<Op, G>(acc);
     op.finish(acc, i, h, gl, writer);
   }
 }
 
-template <class Op, int G>
+template <class Op, int G, bool FILT = false>
 int launch_csr(const peagnn_csr_t& g, const Op& op, cudaStream_t stream, const char* what) {
   const int heads = op.heads;
   if (g.n_heavy > 0) {
     PEAGNN_REQUIRE(g.partial != nullptr && g.heavy_rows && g.heavy_chunk_ptr && g.chunk_row &&
                        g.chunk_begin && g.chunk_end && g.n_chunks > 0,
                    "%s: heavy-row work list incomplete", what);
-    csr_chunk_kernel<Op, G><<<(unsigned)(g.n_chunks * heads), kCtaThreads, 0, stream>>>(g, op);
+    csr_chunk_kernel<Op, G, FILT><<<(unsigned)(g.n_chunks * heads), kCtaThreads, 0, stream>>>(g, op);
     int rc = check_launch(what);
     if (rc) return rc;
   }
@@ -259,9 +312,9 @@ int launch_csr(const peagnn_csr_t& g, const Op& op, cudaStream_t stream, const c
   const long long blocks = heavy_blocks + light_blocks;
   if (blocks == 0) return PEAGNN_OK;
   if (sparse)
-    csr_rows_kernel<Op, G, kSparseRowsPerWarp><<<(unsigned)blocks, kCtaThreads, 0, stream>>>(g, op);
+    csr_rows_kernel<Op, G, kSparseRowsPerWarp, FILT><<<(unsigned)blocks, kCtaThreads, 0, stream>>>(g, op);
   else
-    csr_rows_kernel<Op, G, 1><<<(unsigned)blocks, kCtaThreads, 0, stream>>>(g, op);
+    csr_rows_kernel<Op, G, 1, FILT><<<(unsigned)blocks, kCtaThreads, 0, stream>>>(g, op);
   return check_launch(what);
 }
 

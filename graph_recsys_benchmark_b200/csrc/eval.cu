@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) eval_kernel(
       before += (v > sp) || (v == sp && c < p);
       if (c >= n_pos) {
         win += sp > v;
-        l += neg_log_sigmoid_ref(sp - v);
+        l += neg_log_sigmoid(sp - v);
       }
     }
 #pragma unroll

@@ -84,7 +84,7 @@ struct SpmmOp {
   }
 };
 
-template <int CPL, int G>
+template <int CPL, int G, bool FILT>
 static int run_spmm(const peagnn_csr_t& g, const float* X, int64_t ldx, int feat, float* out,
                     int64_t ldo, const float* rs, const float* cs, int self_loop, const float* bias,
                     int relu, int accumulate, cudaStream_t stream) {
@@ -93,7 +93,7 @@ static int run_spmm(const peagnn_csr_t& g, const float* X, int64_t ldx, int feat
   op.X = X; op.ldx = ldx; op.f4 = feat / 4; op.out = out; op.ldo = ldo;
   op.rs = rs; op.cs = cs; op.bias = bias; op.row_offset = g.row_offset;
   op.self_loop = self_loop && !g.explicit_self_loops; op.relu = relu; op.accumulate = accumulate;
-  return launch_csr<SpmmOp<CPL, G>, G>(g, op, stream, "peagnn_spmm");
+  return launch_csr<SpmmOp<CPL, G>, G, FILT>(g, op, stream, FILT ? "peagnn_spmm_filtered" : "peagnn_spmm");
 }
 
 }  // namespace peagnn
@@ -106,19 +106,18 @@ extern "C" size_t peagnn_partial_floats(int32_t n_chunks, int32_t feat, int32_t 
          (size_t)(4 * ge.CPL + 2);
 }
 
-extern "C" int peagnn_spmm(const peagnn_csr_t* g, const float* X, int64_t ldx, int32_t feat,
-                           float* out, int64_t ldo, const float* rs, const float* cs,
-                           int self_loop, const float* bias, int relu, int accumulate,
-                           peagnn_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  PEAGNN_REQUIRE(g && g->rowptr && (g->col || g->nrows == 0), "peagnn_spmm: null graph");
-  PEAGNN_REQUIRE(feat > 0 && feat % 4 == 0 && feat <= 512, "peagnn_spmm: feat=%d must be a multiple of 4, <= 512", feat);
-  PEAGNN_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0 && ldx >= feat && ldo >= feat, "peagnn_spmm: leading dims must be multiples of 4 and >= feat");
-  PEAGNN_REQUIRE(aligned16(X) && aligned16(out) && (!bias || aligned16(bias)), "peagnn_spmm: pointers must be 16-byte aligned");
-  if (g->nrows == 0) return PEAGNN_OK;
+template <bool FILT>
+static int spmm_dispatch(const peagnn_csr_t& g, const float* X, int64_t ldx, int32_t feat, float* out, int64_t ldo,
+                         const float* rs, const float* cs, int self_loop, const float* bias, int relu, int accumulate,
+                         cudaStream_t stream, const char* what) {
+  PEAGNN_REQUIRE(g.rowptr && (g.col || g.nrows == 0), "%s: null graph", what);
+  PEAGNN_REQUIRE(feat > 0 && feat % 4 == 0 && feat <= 512, "%s: feat=%d must be a multiple of 4, <= 512", what, feat);
+  PEAGNN_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0 && ldx >= feat && ldo >= feat, "%s: leading dims must be multiples of 4 and >= feat", what);
+  PEAGNN_REQUIRE(aligned16(X) && aligned16(out) && (!bias || aligned16(bias)), "%s: pointers must be 16-byte aligned", what);
+  if (g.nrows == 0) return PEAGNN_OK;
   const Geometry ge = geometry_for(feat);
 #define PEAGNN_SPMM_CASE(CPL_, G_) \
-  return run_spmm<CPL_, G_>(*g, X, ldx, feat, out, ldo, rs, cs, self_loop, bias, relu, accumulate, stream)
+  return run_spmm<CPL_, G_, FILT>(g, X, ldx, feat, out, ldo, rs, cs, self_loop, bias, relu, accumulate, stream)
   if (ge.G == 4) PEAGNN_SPMM_CASE(1, 4);
   if (ge.G == 8) PEAGNN_SPMM_CASE(1, 8);
   if (ge.G == 16) PEAGNN_SPMM_CASE(1, 16);
@@ -126,4 +125,51 @@ extern "C" int peagnn_spmm(const peagnn_csr_t* g, const float* X, int64_t ldx, i
   if (ge.CPL == 2) PEAGNN_SPMM_CASE(2, 32);
   PEAGNN_SPMM_CASE(4, 32);
 #undef PEAGNN_SPMM_CASE
+}
+
+extern "C" int peagnn_spmm(const peagnn_csr_t* g, const float* X, int64_t ldx, int32_t feat,
+                           float* out, int64_t ldo, const float* rs, const float* cs,
+                           int self_loop, const float* bias, int relu, int accumulate,
+                           peagnn_stream_t stream_) {
+  PEAGNN_REQUIRE(g, "peagnn_spmm: null graph");
+  peagnn_csr_t view = *g;
+  view.active_rows = view.active_cols = nullptr;
+  return spmm_dispatch<false>(view, X, ldx, feat, out, ldo, rs, cs, self_loop, bias, relu, accumulate,
+                              static_cast<cudaStream_t>(stream_), "peagnn_spmm");
+}
+
+extern "C" int peagnn_spmm_filtered(const peagnn_csr_t* g, const float* X, int64_t ldx, int32_t feat,
+                                    float* out, int64_t ldo, const float* rs, const float* cs, int self_loop,
+                                    const float* bias, int relu, int accumulate, const uint32_t* active_rows,
+                                    const uint32_t* active_cols, peagnn_stream_t stream_) {
+  PEAGNN_REQUIRE(g, "peagnn_spmm_filtered: null graph");
+  peagnn_csr_t view = *g;
+  view.active_rows = active_rows;
+  view.active_cols = active_cols;
+  if (!active_rows && !active_cols)
+    return spmm_dispatch<false>(view, X, ldx, feat, out, ldo, rs, cs, self_loop, bias, relu, accumulate,
+                                static_cast<cudaStream_t>(stream_), "peagnn_spmm_filtered");
+  return spmm_dispatch<true>(view, X, ldx, feat, out, ldo, rs, cs, self_loop, bias, relu, accumulate,
+                             static_cast<cudaStream_t>(stream_), "peagnn_spmm_filtered");
+}
+
+namespace peagnn {
+__global__ void mark_rows_kernel(const int64_t* __restrict__ ids, int64_t n, int mod, int rem, uint32_t* __restrict__ bitmap) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int64_t id = ids[k];
+  if (mod > 1) {
+    if (id % mod != rem) return;
+    id /= mod;
+  }
+  atomicOr(bitmap + (id >> 5), 1u << (id & 31));     // integer OR: order-independent, still deterministic
+}
+}  // namespace peagnn
+
+extern "C" int peagnn_mark_rows(const int64_t* ids, int64_t n, int32_t mod, int32_t rem, uint32_t* bitmap,
+                                peagnn_stream_t stream_) {
+  PEAGNN_REQUIRE(ids && bitmap && n >= 0, "peagnn_mark_rows: bad arguments");
+  if (n == 0) return PEAGNN_OK;
+  mark_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(ids, n, mod, rem, bitmap);
+  return check_launch("peagnn_mark_rows");
 }

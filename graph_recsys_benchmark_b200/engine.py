@@ -29,7 +29,7 @@ class GcnPlan(object):
 
     def __init__(self, model, kind='gcn'):
         n = model.x.shape[0]
-        self.kind = kind
+        self.kind, self.num_nodes = kind, n
         eil = model.meta_path_edge_index_list
         self.P = len(model.pea_channels)
         self.first_graphs, self.rel_of_path = [], []
@@ -82,22 +82,30 @@ class GcnPlan(object):
                 F_.spmm_raw(g.bwd, d, d.shape[1], dx, rs, cs, loop, accumulate=True)
         return dx
 
-    def last_forward(self, t2, z, bias_all):
+    def active_bitmap(self, ids):
+        """Rows of the final representation a loss on the node ids ``ids`` reads (models/base.py:209-210)."""
+        return F_.mark_rows(ids, self.num_nodes)
+
+    def last_forward(self, t2, z, bias_all, active=None):
+        """``active``: only the marked destination rows of the last step are aggregated (the rest of z stays 0)."""
         D, start = self.repr, 0
         for g, members in self.groups:
             width = len(members) * D
             rs, cs, loop = self._scales(g, False)
             F_.spmm_raw(g.fwd, t2[:, start:start + width], width, z[:, start:start + width], rs, cs, loop,
-                        bias_all[start:start + width])
+                        bias_all[start:start + width], active_rows=active)
             start += width
 
-    def last_backward(self, dz):
+    def last_backward(self, dz, active=None):
+        """``active``: dz is zero outside the marked rows, so the transposed pass skips every other edge."""
         dt2 = torch.empty_like(dz)
         D, start = self.repr, 0
         for g, members in self.groups:
             width = len(members) * D
             rs, cs, loop = self._scales(g, True)
-            F_.spmm_raw(g.bwd, dz[:, start:start + width], width, dt2[:, start:start + width], rs, cs, loop)
+            # (the implicit self-loop term of row i reads dz[i], which is zero wherever i is not marked: exact)
+            F_.spmm_raw(g.bwd, dz[:, start:start + width], width, dt2[:, start:start + width], rs, cs, loop,
+                        active_cols=active)
             start += width
         return dt2
 
@@ -135,7 +143,7 @@ class _GcnHead(torch.autograd.Function):
 
 class _GcnBody(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, plan, att, mode, skip, n_rel, *tensors):
+    def forward(ctx, plan, att, mode, skip, n_rel, active, *tensors):
         A1 = [F_._rows(t) for t in tensors[:n_rel]]
         params = tensors[n_rel:]
         P, D, H = plan.P, plan.repr, plan.hidden
@@ -154,9 +162,9 @@ class _GcnBody(torch.autograd.Function):
             s = plan.slot[p]
             F_.linear_raw(h, W2[p], t2[:, s * D:(s + 1) * D], False)
             h1.append(h)
-        z = torch.empty(n, wide, dtype=torch.float32, device=dev)
+        z = (torch.zeros if active is not None else torch.empty)(n, wide, dtype=torch.float32, device=dev)
         bias_all = torch.cat([b2[p] for p in plan.order])
-        plan.last_forward(t2, z, bias_all)
+        plan.last_forward(t2, z, bias_all, active)
         del t2
         att_perm = att.reshape(P, D).index_select(0, plan.order_t).contiguous() if att is not None else None
         out = torch.empty(n, D, dtype=torch.float32, device=dev)
@@ -164,7 +172,7 @@ class _GcnBody(torch.autograd.Function):
         with F_._on(dev):
             F_._lib.call('peagnn_fuse_forward', F_._ptr(z), wide, n, P, D, F_._ptr(att_perm), mode, skip_slot,
                          F_._ptr(out), D, F_._stream())
-        ctx.plan, ctx.mode, ctx.skip, ctx.n_rel = plan, mode, skip, n_rel
+        ctx.plan, ctx.mode, ctx.skip, ctx.n_rel, ctx.active = plan, mode, skip, n_rel, active
         ctx.att_shape = att.shape if att is not None else None
         ctx.save_for_backward(z, att_perm, *A1, *h1, *W1, *W2)
         return out
@@ -194,7 +202,7 @@ class _GcnBody(torch.autograd.Function):
                          dout.stride(0), F_._ptr(dz), wide, F_._ptr(d_att_perm), F_._ptr(ws), need, F_._stream())
         db2_all = torch.empty(wide, dtype=torch.float32, device=dev)
         F_.wgrad_raw(None, dz, 0, wide, 0, None, db2_all)                     # every metapath's d b2 at once
-        dt2 = plan.last_backward(dz)
+        dt2 = plan.last_backward(dz, ctx.active)
         dA1 = [None] * n_rel
         grads = []
         dp1 = torch.empty(n, H, dtype=torch.float32, device=dev)
@@ -219,12 +227,14 @@ class _GcnBody(torch.autograd.Function):
             d_att = torch.empty_like(d_att_perm)
             d_att.index_copy_(0, plan.order_t, d_att_perm)
             d_att = d_att.reshape(ctx.att_shape)
-        return (None, d_att, None, None, None) + tuple(dA1) + tuple(grads)
+        return (None, d_att, None, None, None, None) + tuple(dA1) + tuple(grads)
 
 
-def gcn_forward(model, metapath_idx=None, plan=None):
+def gcn_forward(model, metapath_idx=None, plan=None, active=None):
     """model.forward() through the fused engine (same result as the per-layer path).  With a
-    row-sharded ``plan`` (distributed.ShardedGcnPlan) the result is this rank's rows."""
+    row-sharded ``plan`` (distributed.ShardedGcnPlan) the result is this rank's rows.  With ``active`` (a bitmap
+    from ``plan.active_bitmap``) only the marked rows of the result are computed - the demand-driven form
+    ``loss()`` uses: the last step's aggregation and its transpose touch the batch's rows only."""
     if plan is None:
         plan = getattr(model, '_gcn_plan', None)
         if plan is None:
@@ -237,7 +247,7 @@ def gcn_forward(model, metapath_idx=None, plan=None):
     att = model.att if model.channel_aggr == 'att' else None
     mode = 0 if model.channel_aggr == 'att' else 1
     skip = -1 if metapath_idx is None else int(metapath_idx)
-    return _GcnBody.apply(plan, att, mode, skip, len(a1), *a1, *params)
+    return _GcnBody.apply(plan, att, mode, skip, len(a1), active, *a1, *params)
 
 
 class _SageBody(torch.autograd.Function):
@@ -246,7 +256,7 @@ class _SageBody(torch.autograd.Function):
          Z  = mean_agg(T2) + brel2  (one launch per last-step relation)  + H1 Wroot2^T (accumulated)."""
 
     @staticmethod
-    def forward(ctx, plan, att, mode, skip, n_rel, x, *tensors):
+    def forward(ctx, plan, att, mode, skip, n_rel, active, x, *tensors):
         x = F_._rows(x)
         M1 = [F_._rows(t) for t in tensors[:n_rel]]
         params = [t.contiguous() for t in tensors[n_rel:]]
@@ -263,8 +273,8 @@ class _SageBody(torch.autograd.Function):
             s = plan.slot[p]
             F_.linear_raw(h, wrel2, t2[:, s * D:(s + 1) * D], True)
             h1.append(h)
-        z = torch.empty(n, wide, dtype=torch.float32, device=dev)
-        plan.last_forward(t2, z, torch.cat([par[p][4] for p in plan.order]))
+        z = (torch.zeros if active is not None else torch.empty)(n, wide, dtype=torch.float32, device=dev)
+        plan.last_forward(t2, z, torch.cat([par[p][4] for p in plan.order]), active)
         del t2
         for p in range(P):
             s = plan.slot[p]
@@ -275,7 +285,7 @@ class _SageBody(torch.autograd.Function):
         with F_._on(dev):
             F_._lib.call('peagnn_fuse_forward', F_._ptr(z), wide, n, P, D, F_._ptr(att_perm), mode, skip_slot,
                          F_._ptr(out), D, F_._stream())
-        ctx.plan, ctx.mode, ctx.skip, ctx.n_rel = plan, mode, skip, n_rel
+        ctx.plan, ctx.mode, ctx.skip, ctx.n_rel, ctx.active = plan, mode, skip, n_rel, active
         ctx.att_shape = att.shape if att is not None else None
         ctx.save_for_backward(z, att_perm, x, *M1, *h1, *[w for p in range(P) for w in (par[p][0], par[p][2], par[p][3], par[p][5])])
         return out
@@ -302,7 +312,7 @@ class _SageBody(torch.autograd.Function):
                          dout.stride(0), F_._ptr(dz), wide, F_._ptr(d_att_perm), F_._ptr(wsp), need, F_._stream())
         db2_all = torch.empty(wide, dtype=torch.float32, device=dev)
         F_.wgrad_raw(None, dz, 0, wide, 0, None, db2_all)
-        dt2 = plan.last_backward(dz)
+        dt2 = plan.last_backward(dz, ctx.active)
         dM1 = [None] * n_rel
         dx = None
         grads = []
@@ -338,10 +348,10 @@ class _SageBody(torch.autograd.Function):
             d_att = torch.empty_like(d_att_perm)
             d_att.index_copy_(0, plan.order_t, d_att_perm)
             d_att = d_att.reshape(ctx.att_shape)
-        return (None, d_att, None, None, None, dx) + tuple(dM1) + tuple(grads)
+        return (None, d_att, None, None, None, None, dx) + tuple(dM1) + tuple(grads)
 
 
-def sage_forward(model, metapath_idx=None):
+def sage_forward(model, metapath_idx=None, active=None):
     """model.forward() of a standard PEASage model through the fused engine."""
     plan = getattr(model, '_sage_plan', None)
     if plan is None:
@@ -355,4 +365,4 @@ def sage_forward(model, metapath_idx=None):
     att = model.att if model.channel_aggr == 'att' else None
     mode = 0 if model.channel_aggr == 'att' else 1
     skip = -1 if metapath_idx is None else int(metapath_idx)
-    return _SageBody.apply(plan, att, mode, skip, len(m1), model.x, *m1, *params)
+    return _SageBody.apply(plan, att, mode, skip, len(m1), active, model.x, *m1, *params)

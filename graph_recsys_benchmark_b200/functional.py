@@ -39,19 +39,6 @@ def _ws(n, device):
 # ---------------------------------------------------------------------------------------------
 # raw launches
 # ---------------------------------------------------------------------------------------------
-PROFILE = None     # bench.py sets this to a list: (kernel family, algorithmic bytes, start event, end event)
-
-
-def _timed(name, nbytes, fn):
-    if PROFILE is None:
-        return fn()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    fn()
-    e1.record()
-    PROFILE.append((name, nbytes, e0, e1))
-
-
 def spmm_algorithmic_bytes(nnz, nrows, feat, has_rs, has_cs, self_loop, accumulate=False):
     """every gathered row counted as if it came from HBM, int32 indices,
     fp32 rows: E*(4 col + 4 cs[src] + F*4) + N*(F*4 own row + 4 rs[i] + F*4 write) + (N+1)*4."""
@@ -60,31 +47,61 @@ def spmm_algorithmic_bytes(nnz, nrows, feat, has_rs, has_cs, self_loop, accumula
     return nnz * per_edge + nrows * per_row + (nrows + 1) * 4
 
 
-def spmm_raw(csr, X, feat, out, rs=None, cs=None, self_loop=False, bias=None, relu=False, accumulate=False):
+def spmm_raw(csr, X, feat, out, rs=None, cs=None, self_loop=False, bias=None, relu=False, accumulate=False,
+             active_rows=None, active_cols=None):
+    """One aggregation launch.  ``active_rows`` / ``active_cols`` (bitmaps from ``mark_rows``) switch to the
+    demand-driven entry point: only the marked rows are written / only edges gathering a marked node are read."""
     view = csr.view(feat)
-
-    def launch():
-        with _on(X.device):
-            _lib.call('peagnn_spmm', C.byref(view), _ptr(X), X.stride(0), feat, _ptr(out), out.stride(0),
-                      _ptr(rs), _ptr(cs), int(self_loop), _ptr(bias), int(relu), int(accumulate), _stream())
-    if PROFILE is None:
-        launch()
-    else:
-        nrows = view.nrows
+    tag, nbytes = None, 0
+    filtered = active_rows is not None or active_cols is not None
+    if _lib.profile is not None:
         nnz = csr.nnz if hasattr(csr, 'nnz') else int(csr.rowptr[-1].item() - csr.rowptr[0].item())
-        _timed('spmm_f%d_e%d_n%d_h%d' % (feat, nnz, nrows, view.n_heavy), spmm_algorithmic_bytes(nnz, nrows, feat, rs is not None, cs is not None,
-                                                         self_loop, accumulate), launch)
+        tag = 'spmm%s_f%d_e%d_n%d_h%d' % ('_filtered' if filtered else '', feat, nnz, view.nrows, view.n_heavy)
+        # a filtered launch still walks every index (4 B per edge) but gathers rows only for the marked part, which
+        # is data dependent: its algorithmic bytes are counted as the index walk + one row write per row
+        nbytes = (nnz * 4 + view.nrows * 4 * feat + (view.nrows + 1) * 4) if filtered else \
+            spmm_algorithmic_bytes(nnz, view.nrows, feat, rs is not None, cs is not None, self_loop, accumulate)
+    with _on(X.device):
+        if filtered:
+            _lib.call('peagnn_spmm_filtered', C.byref(view), _ptr(X), X.stride(0), feat, _ptr(out), out.stride(0),
+                      _ptr(rs), _ptr(cs), int(self_loop), _ptr(bias), int(relu), int(accumulate),
+                      _ptr(active_rows), _ptr(active_cols), _stream(), tag=tag, nbytes=nbytes)
+        else:
+            _lib.call('peagnn_spmm', C.byref(view), _ptr(X), X.stride(0), feat, _ptr(out), out.stride(0),
+                      _ptr(rs), _ptr(cs), int(self_loop), _ptr(bias), int(relu), int(accumulate), _stream(),
+                      tag=tag, nbytes=nbytes)
     return out
+
+
+def mark_rows(ids, n_bits, mod=0, rem=0):
+    """Bitmap (int32 words) with bit ``id`` set for every id in ``ids`` (int64, any shape); with ``mod`` > 1 only ids
+    with ``id % mod == rem`` count and their bit index is ``id // mod`` (the local row id under cyclic sharding)."""
+    ids = ids.reshape(-1).contiguous()
+    if ids.dtype != torch.long or not ids.is_cuda:
+        raise TypeError('ids must be a CUDA LongTensor')
+    bitmap = torch.zeros((int(n_bits) + 31) // 32 + 1, dtype=torch.int32, device=ids.device)
+    with _on(ids.device):
+        _lib.call('peagnn_mark_rows', _ptr(ids), ids.numel(), int(mod), int(rem), _ptr(bitmap), _stream())
+    return bitmap
+
+
+def linear_algorithmic_bytes(n, K, M, accumulate=False, gated=False):
+    """X once, Y once, W once (+ Y read when accumulating, + the gate's rows)."""
+    return 4 * n * (K + M) + 4 * K * M + (4 * n * M if accumulate else 0) + (4 * n * M if gated else 0)
 
 
 def linear_raw(X, W, out, w_is_out_in, bias=None, relu=False, accumulate=False, mask=None, out_mask=None):
     n, K = X.shape
     M = out.shape[1]
+    tag, nbytes = None, 0
+    if _lib.profile is not None:
+        tag = 'linear_%dto%d' % (K, M)
+        nbytes = linear_algorithmic_bytes(n, K, M, accumulate, mask is not None or out_mask is not None)
     with _on(X.device):
         _lib.call('peagnn_linear', _ptr(X), X.stride(0), _ptr(mask), mask.stride(0) if mask is not None else 0,
                   n, K, M, _ptr(W), int(w_is_out_in), _ptr(bias), int(relu), int(accumulate),
                   _ptr(out), out.stride(0), _ptr(out_mask), out_mask.stride(0) if out_mask is not None else 0,
-                  _stream())
+                  _stream(), tag=tag, nbytes=nbytes)
     return out
 
 
@@ -92,10 +109,14 @@ def wgrad_raw(X, dY, K, M, w_is_out_in, dW, db, mask=None):
     n = dY.shape[0]
     need = int(_lib.query('peagnn_wgrad_workspace_floats', n, K, M))
     ws = _ws(need, dY.device)
+    tag, nbytes = None, 0
+    if _lib.profile is not None:
+        tag = 'wgrad_%dx%d' % (K, M)
+        nbytes = 4 * n * (K + M) + 4 * K * M + (4 * n * M if mask is not None else 0)
     with _on(dY.device):
         _lib.call('peagnn_linear_wgrad', _ptr(X), X.stride(0) if X is not None else 0, _ptr(dY), dY.stride(0),
                   _ptr(mask), mask.stride(0) if mask is not None else 0, n, K, M, int(w_is_out_in),
-                  _ptr(dW), _ptr(db), _ptr(ws), need, _stream())
+                  _ptr(dW), _ptr(db), _ptr(ws), need, _stream(), tag=tag, nbytes=nbytes)
 
 
 def relu_backward_raw(dy, act):
@@ -280,18 +301,14 @@ class _GatAggregate(torch.autograd.Function):
         denom = torch.empty_like(rowmax)
         out = torch.empty(n, heads * feat, dtype=torch.float32, device=dev)
         view = graph.fwd.view(feat, heads)
-        def launch():
-            with _on(dev):
-                _lib.call('peagnn_gat_aggregate', C.byref(view), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
-                          NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), int(relu), _stream())
+        # E*(4 col + 4 a_j[src] + F*4) + N*(F*4 own row + 8 + F*4 write) + (N+1)*4, per head
+        nnz = graph.fwd.nnz
         with _on(dev):
             _lib.call('peagnn_gat_rowmax', C.byref(view), _ptr(ai), _ptr(aj), heads, NEG_SLOPE, _ptr(rowmax), _stream())
-        if PROFILE is None:
-            launch()
-        else:      # E*(4 col + 4 a_j[src] + F*4) + N*(F*4 own row + 8 + F*4 write) + (N+1)*4, per head
-            nnz = graph.fwd.nnz
-            _timed('gat_f%d_e%d_n%d' % (feat, nnz, n),
-                   heads * (nnz * (8 + 4 * feat) + n * (8 * feat + 8) + (n + 1) * 4), launch)
+            _lib.call('peagnn_gat_aggregate', C.byref(view), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
+                      NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), int(relu), _stream(),
+                      tag='gat_agg_f%d_e%d_n%d' % (feat, nnz, n),
+                      nbytes=heads * (nnz * (8 + 4 * feat) + n * (8 * feat + 8) + (n + 1) * 4))
         ctx.graph, ctx.heads, ctx.relu, ctx.has_bias = graph, heads, relu, bias is not None
         ctx.save_for_backward(H, ai, aj, rowmax, denom, out, bias)
         return out
@@ -418,6 +435,8 @@ class _BprLoss(torch.autograd.Function):
         if batch.dtype != torch.long or batch.dim() != 2 or batch.shape[1] < 3:
             raise ValueError('batch must be a LongTensor [B, >=3]')
         B, cols = int(batch.shape[0]), int(batch.shape[1])
+        if repr_.shape[0] >= 2 ** 31 - 1:
+            raise ValueError('node ids must fit int32 (the gradient scatter sorts 31-bit keys)')
         D = repr_.shape[1]
         dev = repr_.device
         need_grad = any(ctx.needs_input_grad[:5])
@@ -457,10 +476,11 @@ class _EntityReg(torch.autograd.Function):
         need_grad = ctx.needs_input_grad[0]
         loss = torch.zeros(1, dtype=torch.float32, device=dev)
         dx = torch.zeros_like(x) if need_grad else None
-        ws = _ws(B, dev)
+        need = int(_lib.query('peagnn_entity_workspace_floats', B, x.shape[1], int(need_grad)))
+        ws = _ws(need, dev)
         with _on(dev):
             _lib.call('peagnn_entity_reg', _ptr(x), x.stride(0), x.shape[1], _ptr(batch), B, float(coff), _ptr(loss),
-                      int(need_grad), _ptr(dx), dx.stride(0) if need_grad else 0, _ptr(ws), B, _stream())
+                      int(need_grad), _ptr(dx), dx.stride(0) if need_grad else 0, _ptr(ws), need, _stream())
         if need_grad:
             ctx.save_for_backward(dx)
         return loss.reshape(())

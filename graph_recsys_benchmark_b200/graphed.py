@@ -25,14 +25,17 @@ from . import functional as F_
 
 
 class GraphedTrainStep(object):
-    def __init__(self, model, optimizer, example_batch, allreduce=None):
+    def __init__(self, model, optimizer, example_batch, allreduce=None, profile=False):
         """Trains ONE eager step on ``example_batch`` (its loss is ``first_loss``), then captures the step.
         ``allreduce``: optional callable run between backward and the optimizer step (multi-GPU:
-        ``lambda: distributed.allreduce_gradients(params)``)."""
+        ``lambda: distributed.allreduce_gradients(params)``).
+        ``profile``: capture an external CUDA event node on both sides of every C-ABI launch; after each
+        replay (and a synchronize) ``profile_events`` = [(tag, algorithmic bytes, start, end)] holds that
+        replay's per-launch times - measurement builds only, the event nodes serialise the graph."""
         self.model, self.optimizer, self.allreduce = model, optimizer, allreduce
         self.static_batch = example_batch.clone()
         self.shape = tuple(example_batch.shape)
-        saved_profile, F_.PROFILE = F_.PROFILE, None          # timing events cannot live inside a graph
+        self.profile_events = []
         saved_lib_profile, _lib.profile = _lib.profile, None
         try:
             # autograd's AccumulateGrad nodes remember the stream they were created on; nodes born on the
@@ -50,11 +53,13 @@ class GraphedTrainStep(object):
             torch.cuda.synchronize()
             count0 = _lib.load().peagnn_launch_count()
             self.graph = torch.cuda.CUDAGraph()
+            if profile:
+                _lib.profile = self.profile_events
             with torch.cuda.graph(self.graph):
                 self.static_loss = self._eager(self.static_batch)
             self.launches_per_replay = int(_lib.load().peagnn_launch_count() - count0)
         finally:
-            F_.PROFILE, _lib.profile = saved_profile, saved_lib_profile
+            _lib.profile = saved_lib_profile
 
     def _eager(self, batch):
         loss = self.model.loss(batch)

@@ -33,7 +33,14 @@ class GraphRecsysModel(torch.nn.Module):
     def loss(self, pos_neg_pair_t):
         """reference models/base.py:43-80 (BPR sum + entity-aware regulariser on raw x)."""
         if self.training:
-            self.cached_repr = self.forward()
+            if self.demand_driven_loss and self._engine_kind() and getattr(self, '_sharded', None) is None:
+                # only the batch's user / item rows of the representation are read below (models/base.py:209-210):
+                # the last step's aggregation and its transpose run on those rows only; every row that IS computed
+                # equals the full propagation's.  cached_repr is then valid on the batch's rows only.
+                ids = pos_neg_pair_t[:, :3]
+                self.cached_repr = self.forward(_active=self._plan().active_bitmap(ids))
+            else:
+                self.cached_repr = self.forward()
         cf_loss = F_.bpr_loss(self.cached_repr, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
                               pos_neg_pair_t)
         if self.entity_aware and self.training:
@@ -133,6 +140,24 @@ class PEABaseRecsysModel(GraphRecsysModel):
 
     batch_last_step = True     # one aggregation per distinct last-step relation (columns concatenated)
     fused_engine = True        # engine.py: head / body autograd nodes instead of one node per kernel
+    demand_driven_loss = False  # loss() computes only the representation rows its batch reads (BaseSolver turns it on)
+
+    def _engine_kind(self):
+        ok = getattr(self, '_engine_ok', None)
+        if ok is None:
+            from ..engine import GcnPlan
+            ok = self._engine_ok = 'gcn' if GcnPlan.applies(self, 'gcn') else 'sage' if GcnPlan.applies(self, 'sage') else ''
+        return ok if self.fused_engine else ''
+
+    def _plan(self):
+        from ..engine import GcnPlan
+        kind = self._engine_kind()
+        attr = '_gcn_plan' if kind == 'gcn' else '_sage_plan'
+        plan = getattr(self, attr, None)
+        if plan is None:
+            plan = GcnPlan(self, kind)
+            setattr(self, attr, plan)
+        return plan
 
     def channel_outputs(self):
         x = self.x
@@ -157,22 +182,19 @@ class PEABaseRecsysModel(GraphRecsysModel):
                 outs[m] = layer.finish(part, x_in, False)
         return outs
 
-    def forward(self, metapath_idx=None):
+    def forward(self, metapath_idx=None, _active=None):
         """reference models/base.py:191-206.  'att' and 'mean' are the fusions that work upstream
         ('cat' / 'concat' disagree between _init and forward there and raise)."""
         if self.channel_aggr not in ('att', 'mean'):
             raise NotImplementedError('Other aggr methods not implemeted!')
         if getattr(self, '_sharded', None) is not None:      # distributed.shard_model(): row-sharded propagation
             return self._sharded.forward(metapath_idx)
-        if self.fused_engine:                                # whole-model schedule for the standard PEAGCN shape
-            ok = getattr(self, '_engine_ok', None)
-            if ok is None:
-                from ..engine import GcnPlan
-                ok = self._engine_ok = ('gcn' if GcnPlan.applies(self, 'gcn') else
-                                        'sage' if GcnPlan.applies(self, 'sage') else '')
-            if ok:
-                from .. import engine
-                return (engine.gcn_forward if ok == 'gcn' else engine.sage_forward)(self, metapath_idx)
+        ok = self._engine_kind()                             # whole-model schedule for the standard PEAGCN / PEASage shape
+        if ok:
+            from .. import engine
+            if ok == 'gcn':
+                return engine.gcn_forward(self, metapath_idx, plan=self._plan(), active=_active)
+            return engine.sage_forward(self, metapath_idx, active=_active)
         z = torch.stack(self.channel_outputs(), dim=1)                  # [N, P, repr]
         att = self.att if self.channel_aggr == 'att' else None
         return F_.fuse_channels(z, att, self.channel_aggr, metapath_idx)

@@ -88,6 +88,13 @@ typedef struct {
   int32_t explicit_self_loops;    /* != 0: self loops are stored as ordinary edges of the view
                                      (row shards); kernels then add no implicit self loop      */
   int32_t reserved;
+  /* optional per-call filters (NULL = none), bitmaps with bit (id & 31) of word (id >> 5):
+     active_rows - only LOCAL rows whose bit is set are computed and written, the rest are left untouched;
+     active_cols - edges whose gathered node id (col) has a clear bit are skipped (their table rows are
+                   known to be zero, e.g. the gradient rows of nodes outside the batch).
+     peagnn_spmm_filtered() fills them in; peagnn_spmm() and the GAT entry points ignore them. */
+  const uint32_t* active_rows;
+  const uint32_t* active_cols;
 } peagnn_csr_t;
 
 /* Floats of `partial` workspace an aggregation of width F (per head) needs on this view. */
@@ -105,6 +112,23 @@ size_t peagnn_partial_floats(int32_t n_chunks, int32_t feat, int32_t heads);
 int peagnn_spmm(const peagnn_csr_t* g, const float* X, int64_t ldx, int32_t feat,
                 float* out, int64_t ldo, const float* rs, const float* cs, int self_loop,
                 const float* bias, int relu, int accumulate, peagnn_stream_t stream);
+
+/* Demand-driven form of peagnn_spmm (SURVEY.md section 7 "dead rows": GraphRecsysModel.loss reads
+ * only the representation rows of the batch's users and items, models/base.py:209-210).
+ * active_rows != NULL: compute / write only the rows whose bit is set (forward of a last step);
+ * active_cols != NULL: skip the edges that gather a node whose bit is clear (its transpose: the upstream
+ * gradient is zero outside the batch rows).  Same arithmetic and the same in-row edge order as
+ * peagnn_spmm on what remains; no atomics.  Bitmaps: uint32 words, bit (id & 31) of word (id >> 5),
+ * indexed by local row id (active_rows) / gathered node id (active_cols). */
+int peagnn_spmm_filtered(const peagnn_csr_t* g, const float* X, int64_t ldx, int32_t feat,
+                         float* out, int64_t ldo, const float* rs, const float* cs, int self_loop,
+                         const float* bias, int relu, int accumulate, const uint32_t* active_rows,
+                         const uint32_t* active_cols, peagnn_stream_t stream);
+/* bitmap[(id / mod) >> 5] |= 1 << ((id / mod) & 31) for every id with id % mod == rem (mod <= 1: every id,
+ * bit index = id).  bitmap is pre-zeroed by the caller; ids int64 [n].  mod / rem select and renumber the
+ * rows a rank owns under cyclic row sharding. */
+int peagnn_mark_rows(const int64_t* ids, int64_t n, int32_t mod, int32_t rem, uint32_t* bitmap,
+                     peagnn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3: GAT edge-softmax aggregation (models/peagat.py:16-21 -> GATConv).
@@ -207,9 +231,12 @@ int peagnn_predict(const float* repr, int64_t ldr, int32_t D, const int64_t* uni
                    const float* fc2_w, const float* fc2_b, float* scores, peagnn_stream_t stream);
 
 size_t peagnn_bpr_workspace_floats(int64_t B, int32_t D);
-/* loss[0] = -sum_b log sigmoid(score(u,pos) - score(u,neg)).  If need_grad: d_repr (pre-zeroed
- * by the caller, [N, D]) receives atomically-added row gradients, and the fc gradients are
- * written (deterministic two-stage).  All gradients are for d loss = 1. */
+/* loss[0] = -sum_b log sigmoid(score(u,pos) - score(u,neg)), each term evaluated as softplus(-z)
+ * (equal to the reference's sigmoid().log() wherever that is finite, and finite beyond).
+ * If need_grad: the row gradients are ADDED into d_repr ([N, D], pre-zeroed by the caller) in a
+ * fixed order - stable sort of (node id, slot) + one writer per node, no float atomics - and the fc
+ * gradients are written (deterministic two-stage).  Node ids must fit int32.  All gradients are
+ * for d loss = 1; two calls on the same inputs return bit-identical results. */
 int peagnn_bpr_loss(const float* repr, int64_t ldr, int32_t D, const int64_t* batch,
                     int32_t batch_cols, int64_t B, const float* fc1_w, const float* fc1_b,
                     const float* fc2_w, const float* fc2_b, float* loss, int need_grad,
@@ -217,9 +244,11 @@ int peagnn_bpr_loss(const float* repr, int64_t ldr, int32_t D, const int64_t* ba
                     float* d_fc2_b, float* workspace, size_t workspace_floats,
                     peagnn_stream_t stream);
 
+size_t peagnn_entity_workspace_floats(int64_t B, int32_t emb, int need_grad);
 /* loss[0] += coff * ( -sum log sigmoid(mask_i (|x_pos-x_e+|^2 - |x_pos-x_e-|^2))
  *                     -sum log sigmoid(mask_u (|x_u  -x_e+|^2 - |x_u  -x_e-|^2)) );
- * if need_grad, dx (pre-zeroed, [N, emb]) receives coff * gradient by atomic adds. */
+ * if need_grad, coff * gradient is ADDED into dx ([N, emb], pre-zeroed by the caller) in a fixed
+ * order (same sort-based scatter as peagnn_bpr_loss: bit-reproducible, no atomics). */
 int peagnn_entity_reg(const float* x, int64_t ldx, int32_t emb, const int64_t* batch, int64_t B,
                       float coff, float* loss, int need_grad, float* dx, int64_t lddx,
                       float* workspace, size_t workspace_floats, peagnn_stream_t stream);
@@ -264,6 +293,16 @@ int peagnn_bpr_rows(const int64_t* row_ids, int64_t B, const int64_t* u2i, int64
                     const int64_t* ifeat_ptr, const int64_t* ifeat_nids, const int64_t* ufeat_ptr,
                     const int64_t* ufeat_nids, const int64_t* type_starts, int32_t num_types,
                     int64_t* out, peagnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Measurement probe (bench.py / tools/l2_gather_probe.py; no product arithmetic): sums the F-float
+ * rows table[idx[k]] for a coalesced int32 id stream with the aggregation kernels' access pattern
+ * (128-bit loads, F/4 lanes per row) and nothing else - the measured random-row-gather ceiling the
+ * aggregation is reported against.  out needs peagnn_probe_out_floats() floats.  feat in {16,32,64,128}.
+ * ---------------------------------------------------------------------------------------- */
+size_t peagnn_probe_out_floats(void);
+int peagnn_probe_gather(const float* table, int64_t ld, int32_t feat, const int32_t* idx, int64_t n_idx,
+                        float* out, peagnn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -112,15 +112,20 @@ class OraclePEAModel(nn.Module):
         cf = -(pos - neg).sigmoid().log().sum()
         if not (self.entity_aware and self.training):
             return cf
+        # op for op as base.py:56-76 (every x[...] is its own gather, so the gradient of x accumulates
+        # in the reference's order)
         x = self.x
-
-        def sqdist(a, b):
-            d = x[a] - x[b]
-            return (d * d).sum(dim=-1)
-
-        item_arg = (sqdist(t[:, 1], t[:, 3]) - sqdist(t[:, 1], t[:, 4])) * t[:, 5]
-        user_arg = (sqdist(t[:, 0], t[:, 6]) - sqdist(t[:, 0], t[:, 7])) * t[:, 8]
-        reg = -item_arg.sigmoid().log().sum() - user_arg.sigmoid().log().sum()
+        item_pos_reg = (x[t[:, 1]] - x[t[:, 3]]) * (x[t[:, 1]] - x[t[:, 3]])
+        item_neg_reg = (x[t[:, 1]] - x[t[:, 4]]) * (x[t[:, 1]] - x[t[:, 4]])
+        item_pos_reg = item_pos_reg.sum(dim=-1)
+        item_neg_reg = item_neg_reg.sum(dim=-1)
+        user_pos_reg = (x[t[:, 0]] - x[t[:, 6]]) * (x[t[:, 0]] - x[t[:, 6]])
+        user_neg_reg = (x[t[:, 0]] - x[t[:, 7]]) * (x[t[:, 0]] - x[t[:, 7]])
+        user_pos_reg = user_pos_reg.sum(dim=-1)
+        user_neg_reg = user_neg_reg.sum(dim=-1)
+        item_reg = -((item_pos_reg - item_neg_reg) * t[:, 5]).sigmoid().log().sum()
+        user_reg = -((user_pos_reg - user_neg_reg) * t[:, 8]).sigmoid().log().sum()
+        reg = item_reg + user_reg
         return cf + self.entity_aware_coff * reg
 
     def eval(self, metapath_idx=None):                                  # base.py:88-96

@@ -24,18 +24,9 @@ def random_edge_index(n, e, seed, self_loops=0, multi=0, src_range=None, dst_ran
     return torch.stack([src, dst]).long()
 
 
-def model_kwargs(dataset, kind, entity_aware=False, channel_aggr='att', num_heads=1, steps=None,
-                 emb_dim=64, hidden=64, repr_dim=16):
-    from graph_recsys_benchmark_b200.utils import metapath_table
-    P = len(metapath_table({'dataset': dataset.dataset, 'name': dataset.name}))
-    kw = {
-        'model_type': 'Graph', 'if_use_features': False, 'emb_dim': emb_dim, 'hidden_size': hidden,
-        'repr_dim': repr_dim, 'dropout': 0.0, 'meta_path_steps': steps or [2] * P, 'channel_aggr': channel_aggr,
-        'entity_aware': entity_aware, 'entity_aware_coff': 0.1, 'num_nodes': dataset.num_nodes, 'dataset': dataset,
-    }
-    if kind == 'gat':
-        kw['num_heads'] = num_heads
-    return kw
+def model_kwargs(dataset, kind, **kw):
+    from graph_recsys_benchmark_b200.utils.factory import default_model_args
+    return default_model_args(dataset, kind, **kw)
 
 
 def oracle_model_for(dataset, kind, dtype=torch.float32, **kw):
@@ -50,20 +41,96 @@ def oracle_model_for(dataset, kind, dtype=torch.float32, **kw):
 
 
 def product_model_for(dataset, kind, device='cuda', **kw):
-    from graph_recsys_benchmark_b200 import models
-    from graph_recsys_benchmark_b200.utils import update_pea_graph_input
-    base = {'gcn': models.PEAGCNRecsysModel, 'gat': models.PEAGATRecsysModel, 'sage': models.PEASageRecsysModel}[kind]
-    dargs = {'dataset': dataset.dataset, 'name': dataset.name}
-    targs = {'device': device}
-
-    class Model(base):
-        def update_graph_input(self, ds):
-            return update_pea_graph_input(dargs, targs, ds)
-    Model.__name__ = base.__name__
-    return Model(**model_kwargs(dataset, kind, **kw)).to(device)
+    from graph_recsys_benchmark_b200.utils.factory import build_model
+    return build_model(dataset, kind, device=device, **kw)
 
 
 def rel_err(a, b):
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+# ---------------------------------------------------------------------------------------------
+# the run tests/golden/make_reference_fixtures.py performs with the reference's code, restated
+# with the oracle (same seeds, same order of RNG consumption, same outputs)
+# ---------------------------------------------------------------------------------------------
+def state_sha(sd):
+    import hashlib
+    h = hashlib.sha256()
+    for k in sd:
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def tensor_sha(t):
+    import hashlib
+    return hashlib.sha256(t.detach().cpu().contiguous().numpy().tobytes()).hexdigest()
+
+
+def sample_rows(n, k=512):
+    if n <= k:
+        return torch.arange(n)
+    return torch.randperm(n, generator=torch.Generator().manual_seed(0))[:k].sort().values
+
+
+def seed_all(seed):
+    import random as rd
+    rd.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+
+def oracle_run(ds, kind, ea, B, evaluate=True, dtype=torch.float32, run=1, n_steps=3):
+    """Oracle counterpart of ``reference_run`` (tests/golden/make_reference_fixtures.py): every step the
+    reference's code takes there, taken with oracle/ instead."""
+    import hashlib
+    from oracle import sampling as osampling, solver as osolver
+    seed_all(2019 + run)
+    model = oracle_model_for(ds, kind, entity_aware=ea)
+    out = {'state_sha': state_sha(model.state_dict()), 'state': {k: v.clone() for k, v in model.state_dict().items()}}
+    model = model.to(dtype)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-3)
+    train_data = osampling.cf_negative_sampling_bpr(ds, ds.num_negative_samples, ds.sampling_strategy)
+    out['train_rows'] = int(train_data.shape[0])
+    out['train_head'] = train_data[:1000].clone()
+    out['train_sha'] = tensor_sha(train_data)
+    batches = [torch.stack([osampling.getitem(ds, train_data, i, ea) for i in range(s * B, (s + 1) * B)])
+               for s in range(n_steps)]
+    out['batches'] = torch.stack(batches)
+    rows = sample_rows(ds.num_nodes)
+    out['rows'] = rows
+    model.train()
+    losses = []
+    for s in range(n_steps):
+        opt.zero_grad()
+        loss = model.loss(batches[s])
+        loss.backward()
+        if s == 0:
+            out['repr'] = model.cached_repr.detach().clone()
+            out['repr_rows'] = out['repr'][rows].clone()
+            out['repr_abs_sum'] = float(out['repr'].double().abs().sum())
+            grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+            out['x_grad'] = grads['x']
+            out['x_grad_rows'] = grads['x'][rows].clone()
+            out['x_grad_abs_sum'] = float(grads['x'].double().abs().sum())
+            out['grads'] = {k: g for k, g in grads.items() if k != 'x'}
+        opt.step()
+        losses.append(loss.detach().cpu().item())
+    out['losses'] = losses
+    if evaluate:
+        model.eval()
+        out['eval_repr_rows'] = model.cached_repr[rows].clone()
+        np.random.seed(4000 + run)
+        (HR, NDCG, AUC, eloss), per = osolver.metrics(model, ds, 99, return_per_user=True)
+        out['HR'], out['NDCG'], out['AUC'], out['eval_loss'] = HR, NDCG, AUC, eloss
+        out['ranks'] = torch.tensor(per['ranks'], dtype=torch.int16)
+        np.random.seed(4000 + run)
+        cand = np.stack([np.asarray(list(p) + list(n), dtype=np.int64) for p, n in
+                         (osolver.generate_candidates(ds, u, 99) for u in list(ds.test_pos_unid_inid_map.keys()))])
+        out['cand'] = cand
+        out['cand_sha'] = hashlib.sha256(cand.tobytes()).hexdigest()
+        out['cand_head'] = torch.from_numpy(cand[:256].copy())
+    out['model'] = model
+    return out

@@ -56,8 +56,8 @@ def test_plain_c_calls(lib):
 
 def test_csr_struct_layout_matches_header():
     from graph_recsys_benchmark_b200 import _lib
-    # 2 ptr, 4 int32, 2 ptr, 1 int32 (+pad), 3 ptr, 1 ptr on LP64
-    assert ctypes.sizeof(_lib.CsrView) == 8 * 2 + 4 * 4 + 8 * 2 + 8 + 8 * 3 + 8 + 8 + 8
+    # 2 ptr, 4 int32, 2 ptr, 1 int32 (+pad), 3 ptr, 1 ptr, int64, 2 int32, 2 ptr (the optional filters) on LP64
+    assert ctypes.sizeof(_lib.CsrView) == 8 * 2 + 4 * 4 + 8 * 2 + 8 + 8 * 3 + 8 + 8 + 8 + 8 * 2
 
 
 def test_argument_errors_are_reported_not_crashed(lib):

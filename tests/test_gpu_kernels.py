@@ -358,3 +358,78 @@ def test_wgrad_direct(K, M, n, masked, out_in):
     want = X.double().t() @ d
     assert rel_err(outs[0][0], want.t() if out_in else want) < 1e-5
     assert rel_err(outs[0][1], d.sum(0)) < 1e-5
+
+
+# ---- demand-driven aggregation (peagnn_spmm_filtered) and the deterministic gradient scatter -----------------
+@pytest.mark.parametrize('gname', ['small', 'heavy', 'bipartite'])
+@pytest.mark.parametrize('feat', [16, 64, 112])
+def test_filtered_aggregation_equals_the_full_one_on_what_it_computes(gname, feat):
+    from graph_recsys_benchmark_b200 import functional as F_
+    spec = dict(GRAPHS[gname])
+    n = spec.pop('n')
+    ei = random_edge_index(n, spec.pop('e'), 5, self_loops=spec.pop('loops'), multi=spec.pop('multi'), **spec)
+    g = _graph(ei, n)
+    torch.manual_seed(0)
+    X = torch.randn(n, feat, device=DEV)
+    dis = g.gcn_dis
+    full = F_.spmm_raw(g.fwd, X, feat, torch.empty(n, feat, device=DEV), dis, dis, True)
+    ids = torch.randperm(n, device=DEV)[:max(1, n // 7)]
+    bitmap = F_.mark_rows(ids, n)
+    marked = torch.zeros(n, dtype=torch.bool, device=DEV)
+    marked[ids] = True
+    # rows: the marked rows equal the full launch bit for bit, the others are left untouched
+    out = torch.full((n, feat), 7.0, device=DEV)
+    F_.spmm_raw(g.fwd, X, feat, out, dis, dis, True, active_rows=bitmap)
+    assert torch.equal(out[marked], full[marked])
+    assert bool((out[~marked] == 7.0).all())
+    # cols: skipping the edges that gather an unmarked node == aggregating a table whose unmarked rows are zero
+    Xz = X * marked[:, None]
+    want = F_.spmm_raw(g.bwd, Xz, feat, torch.empty(n, feat, device=DEV), dis, dis, True)
+    got = F_.spmm_raw(g.bwd, Xz, feat, torch.empty(n, feat, device=DEV), dis, dis, True, active_cols=bitmap)
+    assert rel_err(got, want) < 1e-6
+    again = F_.spmm_raw(g.bwd, Xz, feat, torch.empty(n, feat, device=DEV), dis, dis, True, active_cols=bitmap)
+    assert torch.equal(got, again)
+
+
+def test_mark_rows_with_cyclic_ownership():
+    from graph_recsys_benchmark_b200 import functional as F_
+    ids = torch.tensor([0, 5, 5, 64, 99, 31, 32], device=DEV)
+    bm = F_.mark_rows(ids, 100).cpu().numpy().view(np.uint32)
+    want = np.zeros_like(bm)
+    for i in (0, 5, 64, 99, 31, 32):
+        want[i >> 5] |= np.uint32(1) << np.uint32(i & 31)
+    assert np.array_equal(bm, want)
+    bm = F_.mark_rows(ids, 34, mod=3, rem=2).cpu().numpy().view(np.uint32)       # ids 5 (-> 1) and 32 (-> 10)
+    want = np.zeros_like(bm)
+    for i in (1, 10):
+        want[i >> 5] |= np.uint32(1) << np.uint32(i & 31)
+    assert np.array_equal(bm, want)
+
+
+def test_bpr_and_entity_gradients_are_bit_reproducible():
+    """The row gradients are scattered by a stable sort + one writer per node (no float atomics)."""
+    from graph_recsys_benchmark_b200 import functional as F_
+    torch.manual_seed(4)
+    n, D, B = 500, 16, 4096
+    rep = torch.randn(n, D, device=DEV, requires_grad=True)
+    fc1w, fc1b = torch.randn(D, 2 * D, device=DEV) * 0.3, torch.randn(D, device=DEV) * 0.1
+    fc2w, fc2b = torch.randn(1, D, device=DEV) * 0.3, torch.randn(1, device=DEV) * 0.1
+    batch = torch.randint(0, n, (B, 9), device=DEV)
+    batch[:, 5] = (batch[:, 5] % 2)
+    batch[:, 8] = (batch[:, 8] % 2)
+    x = torch.randn(n, 64, device=DEV, requires_grad=True)
+    grads = []
+    for _ in range(3):
+        rep.grad = x.grad = None
+        (F_.bpr_loss(rep, fc1w, fc1b, fc2w, fc2b, batch) + F_.entity_reg(x, batch, 0.1)).backward()
+        grads.append((rep.grad.clone(), x.grad.clone()))
+    for a, b in grads[1:]:
+        assert torch.equal(a, grads[0][0]) and torch.equal(b, grads[0][1])
+    # and the loss stays finite where a literal sigmoid().log() overflows in fp32 (z < -88.7)
+    big = torch.zeros(n, D, device=DEV)
+    big[1] = -40.0
+    big[2] = 40.0
+    w1 = torch.cat([torch.zeros(D, D), torch.eye(D)], dim=1).to(DEV)
+    loss = F_.bpr_loss(big, w1, torch.zeros(D, device=DEV), torch.ones(1, D, device=DEV), torch.zeros(1, device=DEV),
+                       torch.tensor([[0, 1, 2]], device=DEV))
+    assert torch.isfinite(loss) and abs(loss.item() - 640.0) < 1e-3        # softplus(640) = 640

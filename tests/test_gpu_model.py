@@ -329,3 +329,35 @@ def test_solver_trains_with_device_sampling_and_cuda_graph(tmp_path):
 def SyntheticHIN_small():
     from graph_recsys_benchmark_b200.datasets import SyntheticHIN
     return SyntheticHIN('tiny', seed=7, sampling_strategy='unseen')
+
+
+@pytest.mark.parametrize('kind', ['gcn', 'sage'])
+@pytest.mark.parametrize('entity_aware', [False, True])
+@pytest.mark.parametrize('shape', ['tiny', 'ml-small'])
+def test_demand_driven_loss_equals_full_propagation(kind, entity_aware, shape):
+    """loss() with ``demand_driven_loss`` computes the last step only on the batch's user / item rows
+    (reference models/base.py:209-210 reads nothing else): same loss, same gradients, and every
+    representation row it does compute is the full propagation's row, bit for bit."""
+    ds = _dataset(shape)
+    batch = _batch(ds, 512, entity_aware).to(DEV)
+    model = product_model_for(ds, kind, entity_aware=entity_aware)
+    model.train()
+    full = model.loss(batch)
+    full.backward()
+    ref_repr = model.cached_repr.detach().clone()
+    ref_grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model.zero_grad()
+    model.demand_driven_loss = True
+    lean = model.loss(batch)
+    lean.backward()
+    rows = torch.unique(batch[:, :3].reshape(-1))
+    assert torch.equal(model.cached_repr.detach()[rows], ref_repr[rows])
+    assert abs(lean.item() - full.item()) <= 1e-6 * abs(full.item())
+    for n, p in model.named_parameters():
+        if float(ref_grads[n].abs().max()) > 1e-12:
+            assert rel_err(p.grad, ref_grads[n]) < 1e-5, n
+    # and it is reproducible run to run
+    model.zero_grad()
+    again = model.loss(batch)
+    again.backward()
+    assert again.item() == lean.item()
