@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-cuda-graph', action='store_true', help='launch every kernel eagerly instead of replaying the captured step')
     ap.add_argument('--no-strong', action='store_true', help='skip the fixed-global-batch leg at N > 1')
+    ap.add_argument('--full-propagation', action='store_true',
+                    help='loss() propagates every row of the last step (the reference\'s literal schedule) instead of the batch rows only')
     ap.add_argument('--prewarm', type=float, default=2.0, help='seconds of untimed steps before the warm-up')
     return ap.parse_args()
 
@@ -138,7 +140,10 @@ def workload_config(args, ds=None, workload=None):
            'arithmetic': 'fp32 storage and accumulation everywhere; the 64/16-wide projections run on the tensor '
                          'cores as a 3-pass TF32 split (hi*hi + hi*lo + lo*hi), fp32-accurate, same 1e-5 parity bound'}
     if args.phase == 'train':
-        cfg.update(batch_per_gpu=args.batch, optimizer='Adam(lr=1e-3, weight_decay=1e-3, fused)', negatives='random')
+        cfg.update(batch_per_gpu=args.batch, optimizer='Adam(lr=1e-3, weight_decay=1e-3, fused)', negatives='random',
+                   last_step_rows=('every row (reference schedule)' if args.full_propagation else
+                                   'the rows loss() reads (the batch\'s users and items, models/base.py:209-210); every '
+                                   'computed value, the loss and all gradients equal the full propagation\'s'))
     return cfg
 
 
@@ -283,6 +288,8 @@ def cpu_baseline_leg(args):
 
 # ---------------------------------------------------------------------------------------------
 def family_of(name):
+    if name.startswith('spmm_filtered'):
+        return 'aggregation_filtered'          # data-dependent work: listed in the breakdown, kept out of the roofline figure
     if name.startswith('spmm') or name.startswith('gat_agg'):
         return 'aggregation'
     if name.startswith('linear') or name.startswith('wgrad'):
@@ -314,15 +321,18 @@ def summarise_profile(records, n_steps):
 
 
 def measure_gather_ceiling(model, ds, dev):
-    """Random-row gather rate of this GPU for the aggregation's own shape: the rows of the (L2-resident)
-    embedding table addressed by the user2item source ids, 64 floats per row, 128-bit loads."""
-    import ctypes as C
+    """Random-row gather rate of this GPU for the dominant aggregation's own access pattern: the very index stream
+    that launch walks (the column array of the forward CSR of the first metapath's first relation - user2item at the
+    MovieLens shapes) addressing the embedding table it gathers from, 128-bit loads, and nothing else."""
     from graph_recsys_benchmark_b200 import _lib
-    from graph_recsys_benchmark_b200.graph import _ptr, _stream
+    from graph_recsys_benchmark_b200.graph import _ptr, _stream, get_graph
     table = model.x.detach()
-    idx = torch.from_numpy(ds.edge_index_nps['user2item'][0].astype(np.int32)).to(dev)
+    g = get_graph(model.meta_path_edge_index_list[0][0], table.shape[0])
+    idx = g.fwd.col
     out = torch.empty(int(_lib.query('peagnn_probe_out_floats')), dtype=torch.float32, device=dev)
     feat = table.shape[1]
+    if feat not in (16, 32, 64, 128) or idx.numel() == 0:
+        return None
 
     def launch():
         _lib.call('peagnn_probe_gather', _ptr(table), table.stride(0), feat, _ptr(idx), idx.numel(), _ptr(out), _stream())
@@ -339,7 +349,8 @@ def measure_gather_ceiling(model, ds, dev):
     nbytes = idx.numel() * (4 + 4 * feat)
     return {'gbs': nbytes / (ms * 1e-3) / 1e9, 'ms': ms, 'rows_gathered': int(idx.numel()), 'row_bytes': 4 * feat,
             'table_mb': table.numel() * 4 / 1e6,
-            'how': 'peagnn_probe_gather: user2item source ids (coalesced int32) -> 128-bit gathers of the embedding table, median of 10'}
+            'how': 'peagnn_probe_gather over the column-index stream of the largest first-step relation (forward CSR) into the '
+                   'embedding table: 128-bit row gathers and a running sum, no row bookkeeping; median of 10, warm L2'}
 
 
 def traffic_from_profiles(kernel_key):
@@ -378,6 +389,7 @@ def run_product(args):
     ds = SyntheticHIN(args.workload, seed=1234)
     torch.manual_seed(2020)
     model = build_model(ds, args.model, device=dev)
+    model.demand_driven_loss = not args.full_propagation
     if world > 1:
         from graph_recsys_benchmark_b200.distributed import shard_model
         shard_model(model, world, rank)
@@ -573,7 +585,7 @@ def product_train(c):
         for f, d in fam.items():
             for name, (cnt, nb, ms) in sorted(d['by_name'].items(), key=lambda kv: -kv[1][2]):
                 sys.stderr.write('PROFILE %-12s %-44s x%6.1f/step %8.3f ms/launch %9.1f GB/s\n'
-                                 % (f, name, cnt / K_r, ms / cnt, nb / (ms / cnt) / 1e6 if ms > 0 else 0.0))
+                                 % (f, name, cnt / K_r, ms / cnt, nb / ms / 1e6 if ms > 0 else 0.0))
     agg_kernel = 'csr_rows_kernel / csr_chunk_kernel (peagnn_spmm' + (', peagnn_gat_aggregate)' if args.model == 'gat' else ')')
     traffic, traffic_src = traffic_from_profiles('%s/%s/aggregation' % (args.workload, args.model)) if world == 1 else (None, None)
     line = {

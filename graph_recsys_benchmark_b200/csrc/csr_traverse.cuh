@@ -65,40 +65,48 @@ __device__ __forceinline__ bool bit_set(const uint32_t* __restrict__ bm, int id)
 }
 
 // Filtered form of process_batches: edges whose gathered node is inactive are dropped before they reach the
-// slots.  A batch of 32 edges costs one coalesced index load, one bitmap probe and a ballot when nothing in
-// it is active (the common case when the filter is a training batch); the survivors keep their order.
+// slots.  Four 32-edge batches are probed per iteration (four independent index loads + bitmap probes in flight:
+// the walk is latency-bound otherwise); a batch with nothing active costs one coalesced index load, one bitmap
+// probe and a ballot - the common case when the filter is a training batch.  The survivors keep their order.
 template <class Op, int G>
 __device__ __forceinline__ void process_batches_filtered(Op& op, const int32_t* __restrict__ col,
                                                          const uint32_t* __restrict__ active, int first, int end,
                                                          int step, float* acc, int lane, int safe_row) {
   constexpr int EPW = 32 / G;
+  constexpr int UN = 4;
   const int gl = lane % G;
   const int slot = lane / G;
-  for (int base = first; base < end; base += step) {
-    const int e = base + lane;
-    int c = safe_row;
-    bool on = false;
-    if (e < end) {
-      c = __ldg(col + e);
-      on = bit_set(active, c);
+  for (int base0 = first; base0 < end; base0 += UN * step) {
+    int c[UN];
+    bool on[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int e = base0 + u * step + lane;
+      c[u] = (base0 + u * step < end && e < end) ? __ldg(col + e) : -1;
     }
-    const unsigned act = __ballot_sync(kFull, on);
-    if (act == 0u) continue;
-    Edge cur;
-    if (on) {
-      cur = op.load_edge(e, c);
-    } else {
-      cur.c = safe_row; cur.w = 0.f; cur.w2 = 0.f;
-    }
-    const int n_act = __popc(act);
-    for (int s = 0; s * EPW < n_act; ++s) {
-      const int k = s * EPW + slot;
-      const bool valid = k < n_act;
-      const int src = (int)__fns(act, 0, valid ? k + 1 : 1);
-      const int cc = __shfl_sync(kFull, cur.c, src);
-      const float w = __shfl_sync(kFull, cur.w, src);
-      const float w2 = Op::kUseW2 ? __shfl_sync(kFull, cur.w2, src) : 0.f;
-      op.apply(acc, base + src, cc, w, w2, gl, valid);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) on[u] = c[u] >= 0 && bit_set(active, c[u]);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const unsigned act = __ballot_sync(kFull, on[u]);
+      if (act == 0u) continue;
+      const int base = base0 + u * step;
+      Edge cur;
+      if (on[u]) {
+        cur = op.load_edge(base + lane, c[u]);
+      } else {
+        cur.c = safe_row; cur.w = 0.f; cur.w2 = 0.f;
+      }
+      const int n_act = __popc(act);
+      for (int s = 0; s * EPW < n_act; ++s) {
+        const int k = s * EPW + slot;
+        const bool valid = k < n_act;
+        const int src = (int)__fns(act, 0, valid ? k + 1 : 1);
+        const int cc = __shfl_sync(kFull, cur.c, src);
+        const float w = __shfl_sync(kFull, cur.w, src);
+        const float w2 = Op::kUseW2 ? __shfl_sync(kFull, cur.w2, src) : 0.f;
+        op.apply(acc, base + src, cc, w, w2, gl, valid);
+      }
     }
   }
 }

@@ -320,8 +320,7 @@ static int dense_mode() {
     if (e && e[0] == 'f') return 0;
     if (e && e[0] == 'm') return 1;
     if (e && e[0] == 'u') return 2;
-    if (e && e[0] == 't') return 5;   // "ts": experimental, untested A-in-TMEM linear (K = 64 shapes)
-    if (e && e[0] == 'p') return 4;   // "pipe": experimental warp-specialised tcgen05 linear (K = 64 shapes)
+    if (e && e[0] == 't') return 5;   // "ts": the A-in-TMEM linear for every K = 64 shape (default: 64 -> 64 only)
     return 3;
   }();
   return mode;
@@ -478,13 +477,11 @@ extern "C" int peagnn_linear(const float* X, int64_t ldx, const float* mask, int
   if (n == 0) return PEAGNN_OK;
   // hot shapes without an input gate: 3xTF32 tensor-core kernels (dense_tc.cuh); PEAGNN_DENSE=ffma keeps
   // the fp32-pipe kernels for A/B timing
-  if (!mask && dense_mode() == 5 && K == 64 && (M == 16 || M == 64)) {
+  // 64 -> 64 (26 launches of a PEAGCN step): the warp-specialised TS-form kernel - 50 us vs 55 us (SS form) at
+  // 291 k rows; 64 -> 16 stays on mma.sync (29 us vs 35 us), profiles/r2_dense.md
+  if (!mask && K == 64 && ((dense_mode() >= 3 && M == 64 && n >= 4096) || (dense_mode() == 5 && (M == 16 || M == 64)))) {
     if (M == 16) return launch_linear_umma_ts<64, 16>(X, ldx, n, W, w_is_out_in, bias, relu, accumulate, Y, ldy, out_mask, ldom, stream);
     return launch_linear_umma_ts<64, 64>(X, ldx, n, W, w_is_out_in, bias, relu, accumulate, Y, ldy, out_mask, ldom, stream);
-  }
-  if (!mask && dense_mode() == 4 && K == 64 && (M == 16 || M == 64)) {
-    if (M == 16) return launch_linear_umma_pipe<64, 16>(X, ldx, n, W, w_is_out_in, bias, relu, accumulate, Y, ldy, out_mask, ldom, stream);
-    return launch_linear_umma_pipe<64, 64>(X, ldx, n, W, w_is_out_in, bias, relu, accumulate, Y, ldy, out_mask, ldom, stream);
   }
   if (!mask && (dense_mode() == 2 || (dense_mode() >= 3 && M == 64)) && (K == 16 || K == 32 || K == 64) &&
       (M == 16 || M == 32 || M == 64)) {

@@ -461,14 +461,16 @@ static int launch_wgrad_umma(const float* X, int64_t ldx, const float* dY, int64
 }
 
 // =================================================================================================
-// EXPERIMENTAL (not dispatched by default; PEAGNN_DENSE=pipe): warp-specialised version of the linear
-// kernel for round 2.  One CTA per SM, 13 warps:
-//   warps 0-7   producers : global -> registers (two tiles ahead) -> hi / lo split -> A stage (2 stages)
+// Warp-specialised TS-form linear kernel (the default for the 64 -> 64 projections; PEAGNN_DENSE=umma selects the
+// SS-form kernel above instead).  One CTA per SM, 13 warps:
+//   warps 0-7   producers : global -> registers (two tiles ahead) -> hi / lo split -> A operand stage
 //   warps 8-11  epilogue  : TMEM accumulator (2 buffers) -> shared staging -> row-contiguous stores
 //   warp  12    MMA       : one thread issues the 3 * K/8 tcgen05.mma of a tile and commits them to the
 //                           stage's "empty" barrier and the accumulator's "full" barrier
-// so the loads, the split, the MMAs and the epilogue of consecutive tiles overlap inside the CTA (the
-// shipped kernel above relies on two co-resident CTAs for that).  Same layouts / descriptors as above.
+// so the loads, the split, the MMAs and the epilogue of consecutive tiles overlap inside the CTA.
+// (An SS-form variant of this pipeline - A_hi / A_lo staged in shared memory - measured 59 us for the 64 -> 64
+// projection of 291 k rows against 55 us for the two-CTA kernel above and 50 us for the TS form below, and was
+// removed: profiles/r2_dense.md.)
 constexpr int kPipeProducerWarps = 8;
 constexpr int kPipeThreads = 32 * (kPipeProducerWarps + 4 + 1);
 
@@ -482,216 +484,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-template <int K, int N>
-__global__ void __launch_bounds__(kPipeThreads, 1) linear_umma_pipe_kernel(
-    const float* __restrict__ X, int64_t ldx, int64_t n_rows, const float* __restrict__ W, int w_is_out_in,
-    const float* __restrict__ bias, int relu, int accumulate, float* __restrict__ Y, int64_t ldy,
-    const float* __restrict__ out_mask, int64_t ldom) {
-  constexpr int BM = 128;
-  constexpr int KC = K / 4, KS = K / 8, CG = KC / 4;
-  constexpr int ITS = 16 * CG / kPipeProducerWarps;       // (8 rows x 4 chunks) blocks per producer warp per tile
-  constexpr uint32_t A_SBO = 128, A_LBO = (BM / 8) * 128;
-  constexpr uint32_t B_SBO = 128, B_LBO = (N / 8) * 128;
-  constexpr int A_BYTES = BM * K * 4, B_BYTES = N * K * 4;
-  constexpr int STAGE_BYTES = 2 * A_BYTES;
-  constexpr uint32_t TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
-  constexpr int SP = N + 4;                                // staging row pitch (floats)
-  static_assert(K % 16 == 0 && N % 16 == 0 && N <= 64 && ITS >= 1 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "unsupported shape");
-  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-  extern __shared__ __align__(128) uint8_t umma_smem[];
-  uint8_t* sStage = umma_smem;                             // [2][A_hi | A_lo]
-  uint8_t* sBh = sStage + 2 * STAGE_BYTES;
-  uint8_t* sBl = sBh + B_BYTES;
-  float* sOut = reinterpret_cast<float*>(sBl + B_BYTES);   // [4 warps][32][SP]
-  __shared__ __align__(8) uint64_t bars[8];                // full[2] empty[2] acc_full[2] acc_empty[2]
-  __shared__ uint32_t tmem_base_slot;
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (threadIdx.x == 32) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&bars[0 + s]), 32 * kPipeProducerWarps);
-      mbar_init(smem_u32(&bars[2 + s]), 1);
-      mbar_init(smem_u32(&bars[4 + s]), 1);
-      mbar_init(smem_u32(&bars[6 + s]), 128);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int idx = threadIdx.x; idx < N * KC; idx += kPipeThreads) {
-    const int j = idx / N, n = idx - j * N;
-    float w[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      w[e] = w_is_out_in ? __ldg(W + (size_t)n * K + 4 * j + e) : __ldg(W + (size_t)(4 * j + e) * N + n);
-    uint4 hi, lo;
-    split_tf32(w[0], hi.x, lo.x); split_tf32(w[1], hi.y, lo.y);
-    split_tf32(w[2], hi.z, lo.z); split_tf32(w[3], hi.w, lo.w);
-    const uint32_t off = (uint32_t)(j * (N / 8) + (n >> 3)) * 128u + (uint32_t)(n & 7) * 16u;
-    *reinterpret_cast<uint4*>(sBh + off) = hi;
-    *reinterpret_cast<uint4*>(sBl + off) = lo;
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = tmem_base_slot;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
-  const uint32_t afull0 = smem_u32(&bars[4]), aempty0 = smem_u32(&bars[6]);
-  const int64_t n_tiles = (n_rows + BM - 1) / BM;
-  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
-  if (warp < kPipeProducerWarps) {
-    // ---------------------------------------------------------------- producers
-    const int rsub = lane & 7, csub = lane >> 3;
-    float4 pre0[ITS], pre1[ITS];
-    auto fetch = [&](int64_t i, float4 (&pre)[ITS]) {
-      const int64_t tile = blockIdx.x + i * gridDim.x;
-#pragma unroll
-      for (int it = 0; it < ITS; ++it) {
-        const int b = warp * ITS + it;
-        const int64_t row = tile * BM + 8 * (b / CG) + rsub;
-        const int chunk = 4 * (b % CG) + csub;
-        pre[it] = (i < my_tiles && row < n_rows) ? ldg4(X + row * ldx + 4 * chunk) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    auto produce = [&](int64_t i, float4 (&pre)[ITS]) {
-      const int s = (int)(i & 1);
-      mbar_wait(empty0 + 8 * s, (uint32_t)(((i >> 1) & 1) ^ 1));     // the MMAs that read this stage two tiles ago are done
-      uint8_t* hi_base = sStage + s * STAGE_BYTES;
-      uint8_t* lo_base = hi_base + A_BYTES;
-#pragma unroll
-      for (int it = 0; it < ITS; ++it) {
-        const int b = warp * ITS + it;
-        const int gi = b / CG, chunk = 4 * (b % CG) + csub;
-        uint4 hi, lo;
-        split_tf32_fast(pre[it].x, hi.x, lo.x); split_tf32_fast(pre[it].y, hi.y, lo.y);
-        split_tf32_fast(pre[it].z, hi.z, lo.z); split_tf32_fast(pre[it].w, hi.w, lo.w);
-        const uint32_t off = (uint32_t)(chunk * (BM / 8) + gi) * 128u + (uint32_t)rsub * 16u;
-        *reinterpret_cast<uint4*>(hi_base + off) = hi;
-        *reinterpret_cast<uint4*>(lo_base + off) = lo;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(full0 + 8 * s);
-      fetch(i + 2, pre);                                              // two tiles ahead, into the registers just drained
-    };
-    fetch(0, pre0);
-    fetch(1, pre1);
-    for (int64_t i = 0; i < my_tiles; i += 2) {
-      produce(i, pre0);
-      if (i + 1 < my_tiles) produce(i + 1, pre1);
-    }
-  } else if (warp == kPipeProducerWarps + 4) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint32_t sb = smem_u32(sStage), bH = smem_u32(sBh), bL = smem_u32(sBl);
-      for (int64_t i = 0; i < my_tiles; ++i) {
-        const int s = (int)(i & 1);
-        const uint32_t par = (uint32_t)((i >> 1) & 1);
-        mbar_wait(full0 + 8 * s, par);                 // the stage is written
-        mbar_wait(aempty0 + 8 * s, par ^ 1);           // the accumulator has been drained
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t aH = sb + s * STAGE_BYTES, aL = aH + A_BYTES;
-#pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          const uint32_t a0 = term == 0 ? aL : aH;
-          const uint32_t b0 = term == 1 ? bL : bH;
-#pragma unroll
-          for (int ks = 0; ks < KS; ++ks)
-            umma_tf32(tmem_base + s * N, umma_desc(a0 + ks * 2 * A_LBO, A_LBO, A_SBO),
-                      umma_desc(b0 + ks * 2 * B_LBO, B_LBO, B_SBO), IDESC, (term | ks) != 0);
-        }
-        umma_commit(empty0 + 8 * s);
-        umma_commit(afull0 + 8 * s);
-      }
-    }
-  } else {
-    // ---------------------------------------------------------------- epilogue (warps 8..11 = TMEM lane quarters 0..3)
-    const int q = warp - kPipeProducerWarps;
-    float* stage = sOut + q * (32 * SP);
-    constexpr int C4 = N / 4;                    // float4 per output row
-    constexpr int RPI = 32 / C4 > 0 ? 32 / C4 : 1;
-    static_assert(C4 <= 32, "one warp instruction covers at least one row");
-    const int c = 4 * (lane % C4);
-    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bias) bv = ldg4(bias + c);
-    for (int64_t i = 0; i < my_tiles; ++i) {
-      const int s = (int)(i & 1);
-      mbar_wait(afull0 + 8 * s, (uint32_t)((i >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      __syncwarp();
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(s * N);
-#pragma unroll
-      for (int u = 0; u < N / 8; ++u) {
-        float v[8];
-        tmem_ld8(taddr + 8 * u, v);
-        st4(stage + lane * SP + 8 * u, make_float4(v[0], v[1], v[2], v[3]));
-        st4(stage + lane * SP + 8 * u + 4, make_float4(v[4], v[5], v[6], v[7]));
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(aempty0 + 8 * s);                // the next-but-one tile's MMAs may overwrite this accumulator
-      __syncwarp();
-      const int64_t tile = blockIdx.x + i * gridDim.x;
-#pragma unroll
-      for (int it = 0; it < 32 / RPI; ++it) {
-        const int r = it * RPI + lane / C4;
-        const int64_t row = tile * BM + 32 * q + r;
-        if (row < n_rows) {
-          float4 o = *reinterpret_cast<const float4*>(stage + r * SP + c);
-          o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-          float* yp = Y + row * ldy + c;
-          if (accumulate) {
-            const float4 p = *reinterpret_cast<const float4*>(yp);
-            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-          }
-          if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          if (out_mask) {
-            const float4 g = ldg4(out_mask + row * ldom + c);
-            o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
-          }
-          st4(yp, o);
-        }
-      }
-      __syncwarp();                                // the staging block is reused by the next tile
-    }
-  }
-
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-}
-
-template <int K, int N>
-static int launch_linear_umma_pipe(const float* X, int64_t ldx, int64_t n, const float* W, int w_is_out_in,
-                                   const float* bias, int relu, int accumulate, float* Y, int64_t ldy,
-                                   const float* out_mask, int64_t ldom, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)4 * (128 * K * 4) + (size_t)2 * (N * K * 4) + (size_t)4 * 32 * (N + 4) * 4 + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(linear_umma_pipe_kernel<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
-  const int64_t tiles = (n + 127) / 128;
-  const int blocks = (int)imin64(tiles, (int64_t)kNumSMs);
-  linear_umma_pipe_kernel<K, N><<<blocks, kPipeThreads, smem, stream>>>(X, ldx, n, W, w_is_out_in, bias, relu, accumulate,
-                                                                      Y, ldy, out_mask, ldom);
-  return check_launch("peagnn_linear(umma pipe)");
-}
-
-
-// =================================================================================================
-// EXPERIMENTAL, UNTESTED ON HARDWARE (compiles; PEAGNN_DENSE=ts selects it; written at the end of round 1
-// when no GPU time was left): the TS form of the same GEMM.  The A operand never touches shared memory: every
+// The TS form of the GEMM.  The A operand never touches shared memory: every
 // producer thread owns one row of the tile (= one TMEM lane), loads it 32 bytes at a time, splits it and
 // writes A_hi / A_lo straight into tensor memory with tcgen05.st; B (the weight matrix) stays in shared
-// memory.  Tests the hypothesis of profiles/r1_dense_tensor_cores.md that the SS-form TF32 MMAs are bound
-// by the shared-memory operand path.  TMEM columns: [0, 2N) two accumulators, then per stage [A_hi (K) | A_lo (K)].
+// memory (round 1's hypothesis that the SS-form TF32 MMAs are held back by the shared-memory operand path: the TS
+// form is 9 % faster at 64 -> 64, parity-green on the 180 linear cases of tests/test_gpu_kernels.py).  TMEM columns: [0, 2N) two accumulators, then per stage [A_hi (K) | A_lo (K)].
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])

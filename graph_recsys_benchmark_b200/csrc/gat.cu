@@ -336,6 +336,7 @@ extern "C" int peagnn_gat_rowmax(const peagnn_csr_t* g, const float* a_i, const 
   RowMaxOp op;
   op.heads = heads; op.a_i = a_i; op.a_j = a_j; op.rowmax = rowmax; op.slope = slope;
   op.row_offset = g->row_offset; op.h_ = 0; op.self_loop = !g->explicit_self_loops;
+  if (g->active_rows) return launch_csr<RowMaxOp, 1, true>(*g, op, stream, "peagnn_gat_rowmax");
   return launch_csr<RowMaxOp, 1>(*g, op, stream, "peagnn_gat_rowmax");
 }
 
@@ -356,6 +357,7 @@ extern "C" int peagnn_gat_aggregate(const peagnn_csr_t* g, const float* H, int64
     op.a_j = a_j; op.rowmax = rowmax; op.denom = denom; op.out = out; op.ldo = ldo;              \
     op.bias = bias; op.slope = slope; op.row_offset = g->row_offset; op.relu = relu;             \
     op.ai_ = 0.f; op.m_ = 0.f; op.h_ = 0; op.self_loop = !g->explicit_self_loops;                \
+    if (g->active_rows) return launch_csr<GatAggOp<CPL_, G_>, G_, true>(*g, op, stream, "peagnn_gat_aggregate"); \
     return launch_csr<GatAggOp<CPL_, G_>, G_>(*g, op, stream, "peagnn_gat_aggregate");           \
   }
   PEAGNN_GEOM_DISPATCH(feat, CALL);
@@ -387,6 +389,7 @@ extern "C" int peagnn_gat_backward_dst(const peagnn_csr_t* g, const float* H, in
     op.row_offset = g->row_offset; op.ai_ = op.m_ = op.inv_den_ = op.D_ = 0.f; op.h_ = 0;          \
     op.self_loop = !g->explicit_self_loops;                                                        \
     for (int q = 0; q < CPL_; ++q) op.g_[q] = make_float4(0.f, 0.f, 0.f, 0.f);                     \
+    if (g->active_rows) return launch_csr<GatBwdDstOp<CPL_, G_>, G_, true>(*g, op, stream, "peagnn_gat_backward_dst"); \
     return launch_csr<GatBwdDstOp<CPL_, G_>, G_>(*g, op, stream, "peagnn_gat_backward_dst");       \
   }
   PEAGNN_GEOM_DISPATCH(feat, CALL);
@@ -411,6 +414,7 @@ extern "C" int peagnn_gat_backward_src(const peagnn_csr_t* gt, const int32_t* pe
     op.alpha_self = alpha_self; op.ds_self = ds_self; op.dout = dout; op.ldd = ldd;                 \
     op.feat = feat; op.f4 = feat / 4; op.dH = dH; op.ldh = ldh; op.d_aj = d_aj;                     \
     op.row_offset = gt->row_offset; op.h_ = 0; op.self_loop = !gt->explicit_self_loops;             \
+    if (gt->active_cols) return launch_csr<GatBwdSrcOp<CPL_, G_>, G_, true>(*gt, op, stream, "peagnn_gat_backward_src"); \
     return launch_csr<GatBwdSrcOp<CPL_, G_>, G_>(*gt, op, stream, "peagnn_gat_backward_src");       \
   }
   PEAGNN_GEOM_DISPATCH(feat, CALL);

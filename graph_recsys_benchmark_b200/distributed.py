@@ -482,13 +482,31 @@ class ShardedPropagation(object):
                 pending[m] = layer.finish(part, loc, False)
         return pending
 
-    def forward(self, metapath_idx=None):
+    def supports_demand_driven(self):
+        return self.kind == 'gcn' and self.model.fused_engine and self._engine_applies()
+
+    def active_bitmap(self, ids):
+        """Bitmap over this rank's LOCAL rows of the representation rows ANY rank's batch reads: the batches are
+        data-parallel, but a rank computes its owned rows for everybody, so the node ids are all-gathered first
+        (3 x B int64 per rank - one small collective)."""
+        ids = ids.reshape(-1).contiguous()
+        world = self.plan.world
+        everyone = torch.empty(world * ids.numel(), dtype=ids.dtype, device=ids.device)
+        if dist.get_backend(self.group) == 'gloo':
+            dist.all_gather(list(everyone.chunk(world)), ids, group=self.group)
+        else:
+            dist.all_gather_into_tensor(everyone, ids, group=self.group)
+        from .engine import ActiveSet
+        return ActiveSet(F_.mark_rows(everyone, self.plan.rows_per_rank, mod=world, rem=self.plan.rank))
+
+    def forward(self, metapath_idx=None, active_ids=None):
         model = self.model
         if self.kind == 'gcn' and model.fused_engine and self._engine_applies():
             from .engine import gcn_forward
             if self._plan is None:
                 self._plan = ShardedGcnPlan(model, self)
-            fused_local = gcn_forward(model, metapath_idx, plan=self._plan)
+            active = self.active_bitmap(active_ids) if active_ids is not None else None
+            fused_local = gcn_forward(model, metapath_idx, plan=self._plan, active=active)
         else:
             z = torch.stack(self.channel_outputs(), dim=1)             # [rows_per_rank, P, repr]
             att = model.att if model.channel_aggr == 'att' else None
@@ -500,6 +518,7 @@ class ShardedPropagation(object):
 class ShardedGcnPlan(object):
     """engine.GcnPlan for row shards: same column layout, the two aggregation phases run on the
     owned rows with ONE all-gather (forward) / reduce-scatter (backward) of the [rows, P*repr] table."""
+    lean_projections = False     # the range / list projection passes are single-GPU only for now
 
     def __init__(self, model, sp):
         self.sp = sp
@@ -548,7 +567,7 @@ class ShardedGcnPlan(object):
                 F_.spmm_raw(rel.bwd('orig'), d, d.shape[1], dx, rel.scale_orig, rel.scale_local, False, accumulate=True)
         return dx
 
-    def last_forward(self, t2, z, bias_all):
+    def last_forward(self, t2, z, bias_all, active=None):
         if self._table is None or self._table.shape != (self.sp.plan.padded, t2.shape[1]):
             self._table = torch.empty(self.sp.plan.padded, t2.shape[1], dtype=torch.float32, device=t2.device)
         table = raw_all_gather(t2, self.sp.group, out=self._table)     # the step's only all-gather
@@ -556,10 +575,11 @@ class ShardedGcnPlan(object):
         for rel, members in self.groups:
             width = len(members) * D
             F_.spmm_raw(rel.fwd('rm'), table[:, start:start + width], width, z[:, start:start + width],
-                        rel.scale_local, rel.scale_rm, False, bias_all[start:start + width])
+                        rel.scale_local, rel.scale_rm, False, bias_all[start:start + width],
+                        active_rows=active.bitmap if active is not None else None)
             start += width
 
-    def last_backward(self, dz):
+    def last_backward(self, dz, active=None):
         if self._dtab is None or self._dtab.shape != (self.sp.plan.padded, dz.shape[1]):
             self._dtab = torch.empty(self.sp.plan.padded, dz.shape[1], dtype=torch.float32, device=dz.device)
         dtab = self._dtab
@@ -567,7 +587,7 @@ class ShardedGcnPlan(object):
         for rel, members in self.groups:
             width = len(members) * D
             F_.spmm_raw(rel.bwd('rm'), dz[:, start:start + width], width, dtab[:, start:start + width],
-                        rel.scale_rm, rel.scale_local, False)
+                        rel.scale_rm, rel.scale_local, False, active_cols=active.bitmap if active is not None else None)
             start += width
         return raw_reduce_scatter(dtab, self.sp.group)                 # ... and its only reduce-scatter
 

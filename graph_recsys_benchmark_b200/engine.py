@@ -23,9 +23,20 @@ from . import functional as F_
 from .graph import get_graph
 
 
+class ActiveSet(object):
+    """The rows of the final representation a loss() call reads (its batch's users and items).
+    ``bitmap``  one bit per node (per LOCAL row on a shard) for the filtered aggregations;
+    ``ids``     the same node ids sorted, duplicates kept ([3B], fixed size: graph-capturable), and
+    ``first``   True at the first occurrence of each id - row lists for the projections (single-GPU plans)."""
+
+    def __init__(self, bitmap, ids=None, first=None):
+        self.bitmap, self.ids, self.first = bitmap, ids, first
+
+
 class GcnPlan(object):
     """Static schedule of a model: which relation feeds which metapath, and the column layout.
     ``kind`` 'gcn' (normalised sum with self loops) or 'sage' (mean over in-edges, no self loops)."""
+    lean_projections = True      # demand-driven loss(): projections on the last step's source range + the active rows
 
     def __init__(self, model, kind='gcn'):
         n = model.x.shape[0]
@@ -54,6 +65,7 @@ class GcnPlan(object):
         self.order_t = torch.tensor(self.order, dtype=torch.long, device=model.x.device)
         first = model.pea_channels[0].gnn_layers
         self.emb, self.hidden, self.repr = first[0].in_channels, first[0].out_channels, first[1].out_channels
+        self._src_range = None
 
     # ---- data movement of the two aggregation phases (overridden by the row-sharded plan) ----------
     def _scales(self, g, transposed):
@@ -84,7 +96,26 @@ class GcnPlan(object):
 
     def active_bitmap(self, ids):
         """Rows of the final representation a loss on the node ids ``ids`` reads (models/base.py:209-210)."""
-        return F_.mark_rows(ids, self.num_nodes)
+        flat = ids.reshape(-1).contiguous()
+        srt = torch.sort(flat).values
+        first = torch.ones_like(srt, dtype=torch.bool)
+        first[1:] = srt[1:] != srt[:-1]
+        return ActiveSet(F_.mark_rows(flat, self.num_nodes), srt, first)
+
+    def source_ranges(self):
+        """Per metapath: [lo, hi) node-id range holding every SOURCE of its last-step relation (node ids are
+        contiguous by type upstream, datasets/movielens.py:184-227, so this is the source type's range; any
+        superset is still exact).  The last step reads the projected table only there and on the active rows."""
+        if self._src_range is None:
+            per_group = []
+            for g, _ in self.groups:
+                col = g.fwd.col
+                per_group.append((int(col.min().item()), int(col.max().item()) + 1) if col.numel() else (0, 0))
+            self._src_range = {}
+            for (g, members), rng in zip(self.groups, per_group):
+                for p in members:
+                    self._src_range[p] = rng
+        return self._src_range
 
     def last_forward(self, t2, z, bias_all, active=None):
         """``active``: only the marked destination rows of the last step are aggregated (the rest of z stays 0)."""
@@ -93,7 +124,7 @@ class GcnPlan(object):
             width = len(members) * D
             rs, cs, loop = self._scales(g, False)
             F_.spmm_raw(g.fwd, t2[:, start:start + width], width, z[:, start:start + width], rs, cs, loop,
-                        bias_all[start:start + width], active_rows=active)
+                        bias_all[start:start + width], active_rows=active.bitmap if active is not None else None)
             start += width
 
     def last_backward(self, dz, active=None):
@@ -105,7 +136,7 @@ class GcnPlan(object):
             rs, cs, loop = self._scales(g, True)
             # (the implicit self-loop term of row i reads dz[i], which is zero wherever i is not marked: exact)
             F_.spmm_raw(g.bwd, dz[:, start:start + width], width, dt2[:, start:start + width], rs, cs, loop,
-                        active_cols=active)
+                        active_cols=active.bitmap if active is not None else None)
             start += width
         return dt2
 
@@ -230,6 +261,141 @@ class _GcnBody(torch.autograd.Function):
         return (None, d_att, None, None, None, None) + tuple(dA1) + tuple(grads)
 
 
+class _GcnBodyLean(torch.autograd.Function):
+    """_GcnBody for a demand-driven loss(): besides aggregating the last step on the active rows only, the
+    per-metapath projections run only where that step reads their result -
+      * the RANGE pass: the node-id range of the last relation's sources (plan.source_ranges(): e.g. the 62 k item
+        rows for the nine ML-25M metapaths that end with item -> user, instead of all 291 k rows), and
+      * the LIST pass: the active rows themselves (the self-loop term), gathered into a [3B, .] buffer.
+    Rows of the range pass that are also on the list are computed twice with the same result; the backward counts each
+    row once (``first`` occurrence, outside the range).  Everything is existing kernels on row slices / gathered
+    rows, fixed shapes, no host sync - the step stays graph-capturable.  Every value that is computed, the loss and
+    all gradients equal _GcnBody's (tests/test_gpu_model.py::test_demand_driven_loss_equals_full_propagation)."""
+
+    @staticmethod
+    def forward(ctx, plan, att, mode, n_rel, active, *tensors):
+        A1 = [F_._rows(t) for t in tensors[:n_rel]]
+        params = tensors[n_rel:]
+        P, D, H = plan.P, plan.repr, plan.hidden
+        W1 = [params[4 * p].contiguous() for p in range(P)]
+        b1 = [params[4 * p + 1].contiguous() for p in range(P)]
+        W2 = [params[4 * p + 2].contiguous() for p in range(P)]
+        b2 = [params[4 * p + 3] for p in range(P)]
+        dev, n, wide = A1[0].device, A1[0].shape[0], P * D
+        ranges = plan.source_ranges()
+        ids, nl = active.ids, int(active.ids.numel())
+        t2 = torch.empty(n, wide, dtype=torch.float32, device=dev)
+        a1c = [None] * n_rel                                   # the active rows of each first-step aggregate
+        h1r, h1c = [], []
+        t2c = torch.empty(nl, wide, dtype=torch.float32, device=dev)
+        for p in range(P):
+            r, s = plan.rel_of_path[p], plan.slot[p]
+            lo, hi = ranges[p]
+            hr = torch.empty(max(hi - lo, 0), H, dtype=torch.float32, device=dev)
+            if hi > lo:
+                F_.linear_raw(A1[r][lo:hi], W1[p], hr, False, b1[p], True)
+                F_.linear_raw(hr, W2[p], t2[lo:hi, s * D:(s + 1) * D], False)
+            if a1c[r] is None:
+                a1c[r] = A1[r].index_select(0, ids)
+            hc = torch.empty(nl, H, dtype=torch.float32, device=dev)
+            F_.linear_raw(a1c[r], W1[p], hc, False, b1[p], True)
+            F_.linear_raw(hc, W2[p], t2c[:, s * D:(s + 1) * D], False)
+            h1r.append(hr)
+            h1c.append(hc)
+        t2.index_copy_(0, ids, t2c)                            # duplicates / range rows rewrite identical values
+        del t2c
+        z = torch.empty(n, wide, dtype=torch.float32, device=dev)     # only the active rows are written, and only they are read
+        bias_all = torch.cat([b2[p] for p in plan.order])
+        plan.last_forward(t2, z, bias_all, active)
+        del t2
+        att_perm = att.reshape(P, D).index_select(0, plan.order_t).contiguous() if att is not None else None
+        # fusion on the active rows only: gathered into [3B, P*D], fused, scattered back (duplicates rewrite the same row)
+        z = z.index_select(0, ids)
+        out_c = torch.empty(nl, D, dtype=torch.float32, device=dev)
+        with F_._on(dev):
+            F_._lib.call('peagnn_fuse_forward', F_._ptr(z), wide, nl, P, D, F_._ptr(att_perm), mode, -1,
+                         F_._ptr(out_c), D, F_._stream())
+        out = torch.zeros(n, D, dtype=torch.float32, device=dev)
+        out.index_copy_(0, ids, out_c)
+        ctx.n_nodes = n
+        ctx.plan, ctx.mode, ctx.n_rel, ctx.active = plan, mode, n_rel, active
+        ctx.att_shape = att.shape if att is not None else None
+        used = [k for k in range(n_rel) if a1c[k] is not None]
+        ctx.used = used
+        ctx.save_for_backward(z, att_perm, *A1, *[a1c[k] for k in used], *h1r, *h1c, *W1, *W2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        plan, n_rel, active = ctx.plan, ctx.n_rel, ctx.active
+        P, D, H, E = plan.P, plan.repr, plan.hidden, plan.emb
+        saved = list(ctx.saved_tensors)
+        z, att_perm = saved[0], saved[1]
+        pos = 2
+        A1 = saved[pos:pos + n_rel]; pos += n_rel
+        a1c = {k: t for k, t in zip(ctx.used, saved[pos:pos + len(ctx.used)])}; pos += len(ctx.used)
+        h1r = saved[pos:pos + P]; pos += P
+        h1c = saved[pos:pos + P]; pos += P
+        W1 = saved[pos:pos + P]; pos += P
+        W2 = saved[pos:pos + P]
+        dev, n, wide = z.device, ctx.n_nodes, P * D
+        ranges = plan.source_ranges()
+        ids, first = active.ids, active.first
+        nl = int(ids.numel())
+        # z holds the gathered active rows; each node's gradient enters once, at its first occurrence on the list
+        dout_c = dout.index_select(0, ids) * first[:, None].to(torch.float32)
+        dz_c = torch.empty(nl, wide, dtype=torch.float32, device=dev)
+        d_att_perm = torch.empty(P, D, dtype=torch.float32, device=dev) if ctx.mode == 0 else None
+        need = int(F_._lib.query('peagnn_fuse_workspace_floats', nl, P, D)) if ctx.mode == 0 else 0
+        ws = F_._ws(need, dev) if ctx.mode == 0 else None
+        with F_._on(dev):
+            F_._lib.call('peagnn_fuse_backward', F_._ptr(z), wide, nl, P, D, F_._ptr(att_perm), ctx.mode, F_._ptr(dout_c),
+                         dout_c.stride(0), F_._ptr(dz_c), wide, F_._ptr(d_att_perm), F_._ptr(ws), need, F_._stream())
+        db2_all = torch.empty(wide, dtype=torch.float32, device=dev)
+        F_.wgrad_raw(None, dz_c, 0, wide, 0, None, db2_all)
+        dz = torch.zeros(n, wide, dtype=torch.float32, device=dev)
+        dz.index_add_(0, ids, dz_c)                            # later occurrences add exact zeros: order-independent
+        dt2 = plan.last_backward(dz, active)
+        dt2c_all = dt2.index_select(0, ids)                    # [3B, wide]: the active rows' gradients, gathered once
+        dA1 = [None] * n_rel
+        grads = []
+        dp1c = torch.empty(nl, H, dtype=torch.float32, device=dev)
+        dac = torch.empty(nl, E, dtype=torch.float32, device=dev)
+        for p in range(P):
+            r, s = plan.rel_of_path[p], plan.slot[p]
+            lo, hi = ranges[p]
+            if dA1[r] is None:
+                dA1[r] = torch.zeros(n, E, dtype=torch.float32, device=dev)
+            dW2, dW1 = torch.empty_like(W2[p]), torch.empty_like(W1[p])
+            db1 = torch.empty(H, dtype=torch.float32, device=dev)
+            if hi > lo:                                        # ---- range pass
+                d_t2 = dt2[lo:hi, s * D:(s + 1) * D]
+                F_.wgrad_raw(h1r[p], d_t2, H, D, False, dW2, None)
+                dp1 = torch.empty(hi - lo, H, dtype=torch.float32, device=dev)
+                F_.linear_raw(d_t2, W2[p], dp1, True, out_mask=h1r[p])
+                F_.wgrad_raw(A1[r][lo:hi], dp1, E, H, False, dW1, db1)
+                F_.linear_raw(dp1, W1[p], dA1[r][lo:hi], True, accumulate=True)
+            else:
+                dW2.zero_(); dW1.zero_(); db1.zero_()
+            # ---- list pass: each active row once (its first occurrence), unless the range pass already took it
+            keep = first & ((ids < lo) | (ids >= hi))
+            d_t2c = dt2c_all[:, s * D:(s + 1) * D] * keep[:, None].to(torch.float32)
+            dW2b, dW1b = torch.empty_like(W2[p]), torch.empty_like(W1[p])
+            db1b = torch.empty(H, dtype=torch.float32, device=dev)
+            F_.wgrad_raw(h1c[p], d_t2c, H, D, False, dW2b, None)
+            F_.linear_raw(d_t2c, W2[p], dp1c, True, out_mask=h1c[p])
+            F_.wgrad_raw(a1c[r], dp1c, E, H, False, dW1b, db1b)
+            F_.linear_raw(dp1c, W1[p], dac, True)
+            dA1[r].index_add_(0, ids, dac)                     # masked-out entries add exact zeros: order-independent
+            grads.extend([dW1 + dW1b, db1 + db1b, dW2 + dW2b, db2_all[s * D:(s + 1) * D]])
+        d_att = None
+        if d_att_perm is not None:
+            d_att = torch.empty_like(d_att_perm)
+            d_att.index_copy_(0, plan.order_t, d_att_perm)
+            d_att = d_att.reshape(ctx.att_shape)
+        return (None, d_att, None, None, None) + tuple(dA1) + tuple(grads)
+
+
 def gcn_forward(model, metapath_idx=None, plan=None, active=None):
     """model.forward() through the fused engine (same result as the per-layer path).  With a
     row-sharded ``plan`` (distributed.ShardedGcnPlan) the result is this rank's rows.  With ``active`` (a bitmap
@@ -247,6 +413,8 @@ def gcn_forward(model, metapath_idx=None, plan=None, active=None):
     att = model.att if model.channel_aggr == 'att' else None
     mode = 0 if model.channel_aggr == 'att' else 1
     skip = -1 if metapath_idx is None else int(metapath_idx)
+    if active is not None and active.ids is not None and skip < 0 and getattr(plan, 'lean_projections', False):
+        return _GcnBodyLean.apply(plan, att, mode, len(a1), active, *a1, *params)
     return _GcnBody.apply(plan, att, mode, skip, len(a1), active, *a1, *params)
 
 

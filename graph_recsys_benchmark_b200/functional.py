@@ -289,18 +289,31 @@ class _GatScores(torch.autograd.Function):
         return dH, d_att_i, d_att_j, None
 
 
+def _filtered_view(view, active_rows=None, active_cols=None):
+    """A copy of a ``peagnn_csr_t`` carrying the demand-driven filters (bitmaps from ``mark_rows``)."""
+    v = _lib.CsrView.from_buffer_copy(view)
+    v.active_rows = active_rows.data_ptr() if active_rows is not None else None
+    v.active_cols = active_cols.data_ptr() if active_cols is not None else None
+    return v
+
+
 class _GatAggregate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, H, ai, aj, bias, graph, heads, relu):
+    def forward(ctx, H, ai, aj, bias, graph, heads, relu, active=None):
+        """``active`` (a bitmap): only the marked target rows are aggregated - the demand-driven last step of
+        loss(); the other rows of the output are zero."""
         H = _rows(_req(H, 'h'))
         n = graph.num_nodes
         feat = H.shape[1] // heads
         dev = H.device
         ai, aj = ai.contiguous(), aj.contiguous()
-        rowmax = torch.empty(n, heads, dtype=torch.float32, device=dev)
-        denom = torch.empty_like(rowmax)
-        out = torch.empty(n, heads * feat, dtype=torch.float32, device=dev)
+        alloc = torch.zeros if active is not None else torch.empty
+        rowmax = alloc(n, heads, dtype=torch.float32, device=dev)
+        denom = alloc(n, heads, dtype=torch.float32, device=dev)
+        out = alloc(n, heads * feat, dtype=torch.float32, device=dev)
         view = graph.fwd.view(feat, heads)
+        if active is not None:
+            view = _filtered_view(view, active_rows=active)
         # SURVEY 8(d): E*(4 col + 4 a_j[src] + F*4) + N*(F*4 own row + 8 + F*4 write) + (N+1)*4, per head
         nnz = graph.fwd.nnz
         with _on(dev):
@@ -309,14 +322,14 @@ class _GatAggregate(torch.autograd.Function):
                       NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), int(relu), _stream(),
                       tag='gat_agg_f%d_e%d_n%d' % (feat, nnz, n),
                       nbytes=heads * (nnz * (8 + 4 * feat) + n * (8 * feat + 8) + (n + 1) * 4))
-        ctx.graph, ctx.heads, ctx.relu, ctx.has_bias = graph, heads, relu, bias is not None
+        ctx.graph, ctx.heads, ctx.relu, ctx.has_bias, ctx.active = graph, heads, relu, bias is not None, active
         ctx.save_for_backward(H, ai, aj, rowmax, denom, out, bias)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         H, ai, aj, rowmax, denom, out, bias = ctx.saved_tensors
-        graph, heads = ctx.graph, ctx.heads
+        graph, heads, active = ctx.graph, ctx.heads, ctx.active
         n = graph.num_nodes
         feat = H.shape[1] // heads
         dev = H.device
@@ -332,13 +345,19 @@ class _GatAggregate(torch.autograd.Function):
         nnz = graph.fwd.nnz
         alpha_e = torch.empty(max(nnz, 1), heads, dtype=torch.float32, device=dev)
         ds_e = torch.empty_like(alpha_e)
-        alpha_s = torch.empty(n, heads, dtype=torch.float32, device=dev)
-        ds_s = torch.empty_like(alpha_s)
-        d_ai = torch.empty_like(alpha_s)
+        # demand-driven: the target-side pass visits the active rows only (dout is zero elsewhere), the source-side
+        # pass skips every edge into an inactive target; per-node outputs of skipped rows must read as zero
+        alloc = torch.zeros if active is not None else torch.empty
+        alpha_s = alloc(n, heads, dtype=torch.float32, device=dev)
+        ds_s = alloc(n, heads, dtype=torch.float32, device=dev)
+        d_ai = alloc(n, heads, dtype=torch.float32, device=dev)
         d_aj = torch.empty_like(alpha_s)
         dH = torch.empty_like(H)
         vf = graph.fwd.view(feat, heads)
         vb = graph.bwd.view(feat, heads)
+        if active is not None:
+            vf = _filtered_view(vf, active_rows=active)
+            vb = _filtered_view(vb, active_cols=active)
         perm = graph.bwd_to_fwd
         with _on(dev):
             _lib.call('peagnn_gat_backward_dst', C.byref(vf), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
@@ -347,15 +366,15 @@ class _GatAggregate(torch.autograd.Function):
             _lib.call('peagnn_gat_backward_src', C.byref(vb), _ptr(perm), _ptr(alpha_e), _ptr(ds_e), _ptr(alpha_s),
                       _ptr(ds_s), _ptr(dout), dout.stride(0), feat, heads, _ptr(dH), dH.stride(0), _ptr(d_aj),
                       _stream())
-        return dH, d_ai, d_aj, db, None, None, None
+        return dH, d_ai, d_aj, db, None, None, None, None
 
 
 def gat_scores(H, att_i, att_j, heads):
     return _GatScores.apply(H, att_i, att_j, heads)
 
 
-def gat_aggregate(H, ai, aj, graph, heads, bias=None, relu=False):
-    return _GatAggregate.apply(H, ai, aj, bias, graph, heads, relu)
+def gat_aggregate(H, ai, aj, graph, heads, bias=None, relu=False, active=None):
+    return _GatAggregate.apply(H, ai, aj, bias, graph, heads, relu, active)
 
 
 # ---------------------------------------------------------------------------------------------

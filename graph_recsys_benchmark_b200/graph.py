@@ -343,7 +343,11 @@ def get_graph(edge_index, num_nodes, keep_self_loops=False):
                 break
     if g is None:
         g = RelationGraph.from_edge_index(edge_index, num_nodes)
-    _by_sig.setdefault(sig, []).append((edge_index, g))
+        # one strong reference per DISTINCT relation (needed to recognise its copies and its flip later); content
+        # hits are not appended again, so rebuilding a model on new device copies does not pin those copies
+        _by_sig.setdefault(sig, []).append((edge_index, g))
+    elif not any(c is g for _, c in _by_sig.get(sig, [])):
+        _by_sig.setdefault(sig, []).append((edge_index, g))       # the flipped orientation of a known relation, once
     import weakref
     _by_ptr[key] = (weakref.ref(edge_index), g)
     return g

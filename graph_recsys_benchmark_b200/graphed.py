@@ -4,8 +4,7 @@ The PEAGNN step is ~270 kernel launches (aggregations, projections, fusion, scor
 GPU the host keeps ahead of the device, but once the propagation is row-sharded over several GPUs each
 rank's kernels shrink and the step becomes launch-bound.  Capturing the step removes the per-launch host
 cost: a replay is a single submission.  Validated on one GPU (tests/test_gpu_model.py, bench.py).  With an
-``allreduce`` hook the NCCL collectives are captured too, but the one 2-GPU trial of round 1 hung, so
-bench.py keeps multi-GPU steps eager until that is understood.
+``allreduce`` hook the NCCL collectives are captured too (capture mode 'thread_local', see __init__).
 
 Contract (the usual CUDA-graph one):
   * run at least one eager step first, so every lazily built structure (CSR views, kernel attributes,
@@ -55,7 +54,11 @@ class GraphedTrainStep(object):
             self.graph = torch.cuda.CUDAGraph()
             if profile:
                 _lib.profile = self.profile_events
-            with torch.cuda.graph(self.graph):
+            # with collectives in the step, NCCL's watchdog thread keeps polling CUDA events of earlier work while this
+            # thread captures; under the default 'global' capture mode that poll is an illegal call and takes the
+            # process group down (the 2-GPU hang of round 1) - 'thread_local' confines the check to this thread
+            mode = 'thread_local' if allreduce is not None or torch.distributed.is_initialized() else 'global'
+            with torch.cuda.graph(self.graph, capture_error_mode=mode):
                 self.static_loss = self._eager(self.static_batch)
             self.launches_per_replay = int(_lib.load().peagnn_launch_count() - count0)
         finally:

@@ -33,12 +33,19 @@ class GraphRecsysModel(torch.nn.Module):
     def loss(self, pos_neg_pair_t):
         """reference models/base.py:43-80 (BPR sum + entity-aware regulariser on raw x)."""
         if self.training:
-            if self.demand_driven_loss and self._engine_kind() and getattr(self, '_sharded', None) is None:
+            sharded = getattr(self, '_sharded', None)
+            if self.demand_driven_loss and sharded is not None and sharded.supports_demand_driven():
+                self.cached_repr = sharded.forward(active_ids=pos_neg_pair_t[:, :3])
+            elif self.demand_driven_loss and sharded is None and self._engine_kind():
                 # only the batch's user / item rows of the representation are read below (models/base.py:209-210):
                 # the last step's aggregation and its transpose run on those rows only; every row that IS computed
                 # equals the full propagation's.  cached_repr is then valid on the batch's rows only.
                 ids = pos_neg_pair_t[:, :3]
                 self.cached_repr = self.forward(_active=self._plan().active_bitmap(ids))
+            elif self.demand_driven_loss and sharded is None and all(ch.supports_active() for ch in self.pea_channels):
+                # per-layer path (PEAGAT): the channels' last conv takes the bitmap
+                bitmap = F_.mark_rows(pos_neg_pair_t[:, :3].reshape(-1), self.x.shape[0])
+                self.cached_repr = self.forward(_active=bitmap)
             else:
                 self.cached_repr = self.forward()
         cf_loss = F_.bpr_loss(self.cached_repr, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
@@ -77,7 +84,10 @@ class PEABaseChannel(torch.nn.Module):
         out = self.forward_split(x, edge_index_list, shared, allow_split=False)
         return out
 
-    def forward_split(self, x, edge_index_list, shared=None, allow_split=True):
+    def supports_active(self):
+        return bool(getattr(self.gnn_layers[-1], 'supports_active', False)) and self.num_steps > 1
+
+    def forward_split(self, x, edge_index_list, shared=None, allow_split=True, active=None):
         """Runs the channel; if the last layer is of the project-then-aggregate kind and
         ``allow_split``, stops after its projection and returns ``(layer, graph, projected, layer_input)``
         so the model can aggregate all channels that share that relation in one launch."""
@@ -97,6 +107,8 @@ class PEABaseChannel(torch.nn.Module):
                     if key not in shared:
                         shared[key] = layer.aggregate_input(x, g)
                     kw['aggregated'] = shared[key]
+            if last and active is not None and getattr(layer, 'supports_active', False):
+                kw['active'] = active                       # demand-driven loss(): only the rows its batch reads
             x = layer(x, ei, relu=not last, graph=g, **kw)
         return x
 
@@ -159,10 +171,10 @@ class PEABaseRecsysModel(GraphRecsysModel):
             setattr(self, attr, plan)
         return plan
 
-    def channel_outputs(self):
+    def channel_outputs(self, active=None):
         x = self.x
         shared = {}
-        outs = [module.forward_split(x, self.meta_path_edge_index_list[idx], shared, self.batch_last_step)
+        outs = [module.forward_split(x, self.meta_path_edge_index_list[idx], shared, self.batch_last_step, active)
                 for idx, module in enumerate(self.pea_channels)]
         groups = {}
         for idx, o in enumerate(outs):
@@ -195,7 +207,7 @@ class PEABaseRecsysModel(GraphRecsysModel):
             if ok == 'gcn':
                 return engine.gcn_forward(self, metapath_idx, plan=self._plan(), active=_active)
             return engine.sage_forward(self, metapath_idx, active=_active)
-        z = torch.stack(self.channel_outputs(), dim=1)                  # [N, P, repr]
+        z = torch.stack(self.channel_outputs(_active), dim=1)           # [N, P, repr]
         att = self.att if self.channel_aggr == 'att' else None
         return F_.fuse_channels(z, att, self.channel_aggr, metapath_idx)
 

@@ -131,7 +131,10 @@ class BaseSolver(object):
         device = self.train_args['device']
         sync_every = self.train_args.get('loss_sync_every', 50)
         model.train()
-        losses, pending, graphed = [], [], None
+        losses, pending = [], []
+        # the captured step is kept across epochs (same model, optimizer and batch shape): one capture per run
+        cached = getattr(self, '_graphed', None)
+        graphed = cached[1] if cached is not None and cached[0] == (id(model), id(optimizer)) else None
         bs = self.train_args['batch_size']
         if self.train_args.get('device_sampling', False):
             # train_args['device_sampling']: negatives and entity columns are drawn on the GPU (sampling.py);
@@ -150,12 +153,13 @@ class BaseSolver(object):
             if max_steps is not None and step >= max_steps:
                 break
             batch = batch.to(device, non_blocking=True)
-            if self.train_args.get('cuda_graph', False) and step > 0:
+            if self.train_args.get('cuda_graph', False) and (step > 0 or graphed is not None):
                 # train_args['cuda_graph']: after one eager step the whole step is replayed as one CUDA graph
                 # (graphed.py; the optimizer must have been built with capturable=True)
                 if graphed is None:
                     from .graphed import GraphedTrainStep
                     graphed = GraphedTrainStep(model, optimizer, batch)    # trains on this batch, then captures
+                    self._graphed = ((id(model), id(optimizer)), graphed)
                     pending.append(graphed.first_loss)
                 else:
                     pending.append(graphed(batch).clone())
@@ -173,6 +177,35 @@ class BaseSolver(object):
         if pending:
             losses.extend(torch.stack(pending).cpu().tolist())
         return float(np.mean(losses)) if losses else float('nan'), losses
+
+    def _post_run_ablation(self, dataset, logger_file):
+        """reference solvers.py:333-392: after all runs, reload run 1's latest checkpoint and evaluate the model
+        with each metapath's channel zeroed in turn ('exclude path' lines)."""
+        run = 1
+        epoch = 20 if self.dataset_args['dataset'] == 'Yelp' else 30
+        seed = 2019 + run
+        rd.seed(seed)
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        torch.cuda.manual_seed(seed)
+        self.model_args['num_nodes'] = dataset.num_nodes
+        self.model_args['dataset'] = dataset
+        model = self.model_class(**self.model_args).to(self.train_args['device'])
+        optimizer = get_opt_class(self.train_args['opt'])(params=model.parameters(), lr=self.train_args['lr'],
+                                                          weight_decay=self.train_args['weight_decay'])
+        weights_path = os.path.join(self.train_args['weights_folder'], 'run_{}'.format(str(run)))
+        os.makedirs(weights_path, exist_ok=True)
+        model, optimizer, _, _ = load_model(os.path.join(weights_path, 'latest.pkl'), model, optimizer,
+                                            self.train_args['device'])
+        for metapath_idx in range(len(self.model_args['meta_path_steps'])):
+            model.eval(metapath_idx)
+            HRs, NDCGs, AUC, _ = self.metrics(run, epoch, model, dataset)
+            msg = 'Run: {}, epoch: {}, exclude path:{}, '.format(run, epoch, metapath_idx) + _fmt_metrics(HRs, NDCGs, AUC) + '\n'
+            print(msg)
+            logger_file.write(msg)
+            instantwrite(logger_file)
+        del model, optimizer
+        clearcache()
 
     def run(self):
         global_logger_path = self.train_args['logger_folder']
@@ -205,6 +238,9 @@ class BaseSolver(object):
                         raise NotImplementedError('only the PEAGNN graph models are in scope')
 
                     model = self.model_class(**self.model_args).to(self.train_args['device'])
+                    # train_args['demand_driven_loss'] (default on): loss() computes only the representation rows
+                    # its batch reads - same loss and gradients as the full propagation of models/base.py:45
+                    model.demand_driven_loss = bool(self.train_args.get('demand_driven_loss', True))
 
                     opt_class = get_opt_class(self.train_args['opt'])
                     opt_kwargs = {'capturable': True} if self.train_args.get('cuda_graph', False) else {}
@@ -297,7 +333,13 @@ class BaseSolver(object):
                     instantwrite(logger_file)
 
                     del model, optimizer, rec_metrics
+                    from .graph import clear_cache
+                    clear_cache()                      # the next run's model builds its own device copies of the relations
+                    self._graphed = None
                     clearcache()
+
+            if str(self.dataset_args.get('model', ''))[:3] == 'PEA' and self.train_args['metapath_test']:
+                self._post_run_ablation(dataset, logger_file)
 
             msg = 'Overall HR@5: {:.4f}, HR@10: {:.4f}, HR@15: {:.4f}, HR@20: {:.4f}, ' \
                   'NDCG@5: {:.4f}, NDCG@10: {:.4f}, NDCG@15: {:.4f}, NDCG@20: {:.4f}, AUC: {:.4f}, ' \

@@ -92,7 +92,9 @@ typedef struct {
      active_rows - only LOCAL rows whose bit is set are computed and written, the rest are left untouched;
      active_cols - edges whose gathered node id (col) has a clear bit are skipped (their table rows are
                    known to be zero, e.g. the gradient rows of nodes outside the batch).
-     peagnn_spmm_filtered() fills them in; peagnn_spmm() and the GAT entry points ignore them. */
+     peagnn_spmm_filtered() fills them in and peagnn_spmm() ignores them; the GAT entry points honour what the
+     view carries: active_rows in peagnn_gat_rowmax / _aggregate / _backward_dst (rows outside are not computed;
+     their outputs must be pre-zeroed by the caller), active_cols in peagnn_gat_backward_src. */
   const uint32_t* active_rows;
   const uint32_t* active_cols;
 } peagnn_csr_t;

@@ -25,7 +25,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, kind, entity_aware, ret, shape='tiny', backend='gloo', B=256):
+def _worker(rank, world, port, kind, entity_aware, ret, shape='tiny', backend='gloo', B=256, fixture=None):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dev = rank if backend == 'nccl' else 0
@@ -48,8 +48,25 @@ def _worker(rank, world, port, kind, entity_aware, ret, shape='tiny', backend='g
         import random, numpy as np
         random.seed(1); np.random.seed(1); torch.manual_seed(1)
         ds.cf_negative_sampling()
+        B -= B % world                                         # equal per-rank batches (data-parallel)
         full = ds.get_batch(list(range(B))).cuda()
         mine = full[rank::world].contiguous()                  # data-parallel split of the global batch
+        truth = None
+        if fixture is not None:
+            # the reference's own run of this configuration (tests/golden/reference_runs.pt): same parameters,
+            # same global batch, gradients from the reference code in fp64 - the ground truth for BOTH models below
+            from helpers import oracle_model_for, seed_all, state_sha
+            fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_runs.pt'),
+                            weights_only=False)[fixture]
+            seed_all(2019 + 1)
+            oracle = oracle_model_for(ds, kind.split('-')[0], entity_aware=entity_aware)
+            assert state_sha(oracle.state_dict()) == fx['f32']['state_sha']
+            model.load_state_dict(oracle.state_dict())
+            full = fx['f32']['batches'][0].long().cuda()
+            B = full.shape[0] - full.shape[0] % world
+            full = full[:B].contiguous()
+            mine = full[rank::world].contiguous()
+            truth = fx['f64'] if B == fx['f32']['batches'].shape[1] else None
         model.train()
         ref_state = {k: v.clone() for k, v in model.state_dict().items()}
         # unsharded reference on the whole global batch (same process, rank 0 only reports it)
@@ -68,6 +85,33 @@ def _worker(rank, world, port, kind, entity_aware, ret, shape='tiny', backend='g
 
         def rel(a, b):
             return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
+        first = dict(loss=abs(total.item() - loss_ref.item()) / abs(loss_ref.item()),
+                     repr=rel(model.cached_repr, ref_repr),
+                     grads={n: rel(p.grad, ref_grads[n]) for n, p in model.named_parameters()
+                            if float(ref_grads[n].abs().max()) > 1e-10})
+        vs_truth = None
+        if truth is not None:
+            named = dict(model.named_parameters())
+            vs_truth = dict(
+                loss_sharded=abs(total.item() - truth['losses'][0]) / abs(truth['losses'][0]),
+                loss_unsharded=abs(loss_ref.item() - truth['losses'][0]) / abs(truth['losses'][0]),
+                sharded={n: rel(named[n].grad, g.cuda()) for n, g in truth['grads'].items() if float(g.abs().max()) > 1e-10},
+                unsharded={n: rel(ref_grads[n], g.cuda()) for n, g in truth['grads'].items() if float(g.abs().max()) > 1e-10})
+        dd = None
+        if model._sharded.supports_demand_driven():
+            # the demand-driven loss on shards: the union of every rank's batch rows is aggregated, nothing else
+            model.zero_grad()
+            model.demand_driven_loss = True
+            loss2 = model.loss(mine)
+            loss2.backward()
+            allreduce_gradients(list(model.parameters()))
+            total2 = loss2.detach().clone()
+            dist.all_reduce(total2)
+            torch.cuda.synchronize()
+            dd = dict(loss=abs(total2.item() - loss_ref.item()) / abs(loss_ref.item()),
+                      grads={n: rel(p.grad, ref_grads[n]) for n, p in model.named_parameters()
+                             if float(ref_grads[n].abs().max()) > 1e-10})
+            model.demand_driven_loss = False
         # evaluation: users sharded over ranks + all-reduce of the partial sums == all users on one rank
         from graph_recsys_benchmark_b200.solvers import BaseSolver
         solver = BaseSolver(None, {}, {}, {'device': 'cuda:%d' % dev, 'num_neg_candidates': 99, 'batch_size': 128})
@@ -78,13 +122,7 @@ def _worker(rank, world, port, kind, entity_aware, ret, shape='tiny', backend='g
         (hr_s, nd_s, auc_s, l_s), _ = solver.metrics(1, 1, model, ds, return_per_user=True)
         eval_gap = max(float(np.abs(hr_d - hr_s).max()), float(np.abs(nd_d - nd_s).max()),
                        float(np.abs(auc_d - auc_s).max()), float(np.abs(l_d - l_s).max() / abs(l_s[0])))
-        ret[rank] = dict(
-            eval_gap=eval_gap, finite=bool(torch.isfinite(total).item()),
-            loss=abs(total.item() - loss_ref.item()) / abs(loss_ref.item()),
-            repr=rel(model.cached_repr, ref_repr),
-            grads={n: rel(p.grad, ref_grads[n]) for n, p in model.named_parameters()
-                   if float(ref_grads[n].abs().max()) > 1e-10},
-        )
+        ret[rank] = dict(eval_gap=eval_gap, finite=bool(torch.isfinite(total).item()), dd=dd, vs_truth=vs_truth, **first)
     finally:
         dist.destroy_process_group()
 
@@ -105,8 +143,23 @@ def _check(ret, world):
         assert out['loss'] < 1e-5, out
         assert out['eval_gap'] < 1e-12, out
         assert out['repr'] < 1e-5, out
+        vt = out.get('vs_truth')
+        if vt is not None:
+            # judged against the reference's fp64 run: the sharded model has to meet the same bound as the unsharded one
+            worst_s = max(vt['sharded'].items(), key=lambda kv: kv[1])
+            worst_u = max(vt['unsharded'].items(), key=lambda kv: kv[1])
+            if r == 0:
+                print('vs reference fp64: loss sharded %.2e / unsharded %.2e; worst gradient sharded %s %.2e, unsharded %s %.2e'
+                      % (vt['loss_sharded'], vt['loss_unsharded'], worst_s[0], worst_s[1], worst_u[0], worst_u[1]))
+            assert vt['loss_sharded'] < 1e-5, vt
+            assert worst_s[1] < 1e-4, (worst_s, worst_u)
+            continue                # two fp32 sums in different orders are each within the bound of the truth, not of each other
         for name, e in out['grads'].items():
             assert e < 1e-4, (name, e)
+        if out['dd'] is not None:
+            assert out['dd']['loss'] < 1e-5, out['dd']
+            for name, e in out['dd']['grads'].items():
+                assert e < 1e-4, ('demand-driven', name, e)
 
 
 def test_eight_way_shards_of_the_25m_shaped_graph_match_unsharded():
@@ -115,7 +168,8 @@ def test_eight_way_shards_of_the_25m_shaped_graph_match_unsharded():
     on the same global batch of 4096 triples."""
     world = 8
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), 'gcn', False, ret, 'ml-25m-lite', 'gloo', 4096), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), 'gcn', False, ret, 'ml-25m-lite', 'gloo', 4096, 'ml-25m-lite/gcn/plain'),
+             nprocs=world, join=True)
     _check(ret, world)
 
 
@@ -126,7 +180,8 @@ def test_nccl_sharded_model_matches_unsharded(kind, world):
     if torch.cuda.device_count() < world:
         pytest.skip('needs %d GPUs, this box has %d' % (world, torch.cuda.device_count()))
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), kind, False, ret, 'ml-25m-lite', 'nccl', 4096), nprocs=world, join=True)
+    fixture = 'ml-25m-lite/gcn/plain' if kind == 'gcn' else None
+    mp.spawn(_worker, args=(world, _free_port(), kind, False, ret, 'ml-25m-lite', 'nccl', 4096, fixture), nprocs=world, join=True)
     _check(ret, world)
 
 

@@ -177,7 +177,8 @@ def test_fused_engine_equals_layer_path(kind, aggr, entity_aware):
     assert rel_err(res[True][1], res[False][1]) < 1e-6
     for n, g in res[False][2].items():
         if float(g.abs().max()) > 1e-12:
-            assert rel_err(res[True][2][n], g) < 1e-5, n
+            # two fp32 schedules of the same sums (each within 1e-5 of the fp64 oracle, test_model_loss_and_all_gradients)
+            assert rel_err(res[True][2][n], g) < 2e-5, n
     for idx in (0, 4):                                   # ablation goes through the engine too
         outs = []
         for fused in (True, False):
@@ -331,7 +332,7 @@ def SyntheticHIN_small():
     return SyntheticHIN('tiny', seed=7, sampling_strategy='unseen')
 
 
-@pytest.mark.parametrize('kind', ['gcn', 'sage'])
+@pytest.mark.parametrize('kind', ['gcn', 'sage', 'gat'])
 @pytest.mark.parametrize('entity_aware', [False, True])
 @pytest.mark.parametrize('shape', ['tiny', 'ml-small'])
 def test_demand_driven_loss_equals_full_propagation(kind, entity_aware, shape):
