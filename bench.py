@@ -320,6 +320,15 @@ def summarise_profile(records, n_steps):
     return fam
 
 
+def dominant_launch(fam, hbm_peak, gather):
+    """The launch tag with the most algorithmic bytes in a family, with its own rate (the family figure averages
+    it with the small, latency-bound relations)."""
+    name, (cnt, nb, ms) = max(fam['by_name'].items(), key=lambda kv: kv[1][1] / kv[1][0])
+    gbs = nb / (ms * 1e-3) / 1e9 if ms > 0 else None
+    return {'tag': name, 'launches': cnt, 'bytes_per_launch': nb / cnt, 'ms_per_launch': ms / cnt, 'achieved': gbs,
+            'frac': gbs / hbm_peak if gbs else None, 'frac_of_l2_gather_ceiling': (gbs / gather['gbs']) if (gbs and gather) else None}
+
+
 def measure_gather_ceiling(model, ds, dev):
     """Random-row gather rate of this GPU for the dominant aggregation's own access pattern: the very index stream
     that launch walks (the column array of the forward CSR of the first metapath's first relation - user2item at the
@@ -521,6 +530,8 @@ def product_train(c):
         for gr in opt.param_groups:
             gr['lr'] = 0.0                                        # measurement only: do not move the weights further
         inst = None
+        from graph_recsys_benchmark_b200 import engine as _engine
+        _engine.PARALLEL_BRANCHES = False       # per-kernel events need the launches one after the other
         if graphed is not None:
             try:
                 inst = GraphedTrainStep(model, opt, dev_batches[0], profile=True)
@@ -537,8 +548,9 @@ def product_train(c):
                 torch.cuda.synchronize()                          # the graph's event nodes are re-recorded by every replay
                 records.extend((n, b, a.elapsed_time(z)) for n, b, a, z in inst.profile_events)
             r1.record()
-            roof_how = ('external CUDA event nodes inside %d replays of the step graph re-captured with them '
-                        '(one synchronize per replay to read them)' % K_r)
+            roof_how = ('external CUDA event nodes inside %d replays of the step graph re-captured with them and with its '
+                        'parallel branches serialised, so every launch is timed alone (one synchronize per replay to read '
+                        'them); the event nodes themselves make this graph slower than the timed one' % K_r)
         else:
             _lib.profile = []
             r0.record()
@@ -550,6 +562,7 @@ def product_train(c):
             _lib.profile = None
             roof_how = 'CUDA events around every launch of %d eager steps' % K_r
         barrier()
+        _engine.PARALLEL_BRANCHES = True
         ms_roof = r0.elapsed_time(r1) / K_r
         for gr in opt.param_groups:
             gr['lr'] = 1e-3
@@ -612,6 +625,7 @@ def product_train(c):
                      'tables (<= 75 MB) live in the 126 MB L2, so a fraction above 1 of the HBM copy peak is expected - the '
                      'ceiling that binds is the L2 random-row gather rate, measured live below'),
             'l2_gather_ceiling': gather, 'frac_of_l2_gather_ceiling': (ach / gather['gbs']) if gather else None,
+            'dominant_launch': dominant_launch(agg, c['hbm_peak'], gather),
             'launches_per_step': agg['launches_per_step'], 'ms_per_step': agg['ms_per_step'],
             'share_of_step': agg['ms_per_step'] / ms_roof if ms_roof else None,
             'events': roof_how, 'instrumented_ms_per_step': ms_roof,

@@ -547,11 +547,15 @@ class ShardedGcnPlan(object):
         self._table = self._dtab = None
 
     def head_forward(self, x):
+        from .engine import _Fork
         rpr = self.sp.plan.rows_per_rank
-        outs = []
+        outs = [torch.empty(rpr, x.shape[1], dtype=torch.float32, device=x.device) for _ in self.first_rels]
         for rel in self.first_rels:
-            out = torch.empty(rpr, x.shape[1], dtype=torch.float32, device=x.device)
-            outs.append(F_.spmm_raw(rel.fwd('orig'), x, x.shape[1], out, rel.scale_local, rel.scale_orig, False))
+            rel.fwd('orig').view(x.shape[1])                     # structures / workspaces are built on this stream, before the fork
+        with _Fork(x.device) as fork:                            # independent launches on this rank's shards: parallel branches
+            for k, (rel, out) in enumerate(zip(self.first_rels, outs)):
+                with fork.on(k):
+                    F_.spmm_raw(rel.fwd('orig'), x, x.shape[1], out, rel.scale_local, rel.scale_orig, False)
         return outs
 
     def head_backward(self, grads):

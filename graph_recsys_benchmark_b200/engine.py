@@ -23,6 +23,50 @@ from . import functional as F_
 from .graph import get_graph
 
 
+_side_streams = {}
+PARALLEL_BRANCHES = True      # False: _Fork runs its branches in order on the current stream (per-kernel timing builds)
+
+
+def fork_streams(device, n_streams=4):
+    key = (device.index, n_streams)
+    if key not in _side_streams:
+        _side_streams[key] = [torch.cuda.Stream(device=device) for _ in range(n_streams)]
+    return _side_streams[key]
+
+
+class _Fork(object):
+    """Independent kernel chains on side streams: fork from the current stream on entry, join back on exit.
+    The 13 per-metapath projection chains of a demand-driven step are many small launches (a few hundred rows
+    to 62 k rows each); issued back to back on one stream every one of them pays its own ramp-up and tail, on
+    parallel branches they fill the GPU together.  Inside a CUDA-graph capture the branches become parallel
+    paths of the graph.  Buffers that outlive the block are allocated by the caller BEFORE entering it."""
+
+    def __init__(self, device, n_streams=4):
+        self.streams = fork_streams(device, n_streams)
+        self.device = device
+
+    def __enter__(self):
+        self.parallel = PARALLEL_BRANCHES
+        if self.parallel:
+            self.main = torch.cuda.current_stream(self.device)
+            ev = self.main.record_event()
+            for st in self.streams:
+                st.wait_event(ev)
+        return self
+
+    def on(self, k):
+        if not self.parallel:
+            import contextlib
+            return contextlib.nullcontext()
+        return torch.cuda.stream(self.streams[k % len(self.streams)])
+
+    def __exit__(self, *exc):
+        if self.parallel:
+            for st in self.streams:
+                self.main.wait_stream(st)
+        return False
+
+
 class ActiveSet(object):
     """The rows of the final representation a loss() call reads (its batch's users and items).
     ``bitmap``  one bit per node (per LOCAL row on a shard) for the filtered aggregations;
@@ -67,6 +111,13 @@ class GcnPlan(object):
         self.emb, self.hidden, self.repr = first[0].in_channels, first[0].out_channels, first[1].out_channels
         self._src_range = None
 
+    def source_range_tensors(self, dev):
+        if getattr(self, '_range_t', None) is None:
+            ranges = self.source_ranges()
+            self._range_t = (torch.tensor([ranges[p][0] for p in self.order], dtype=torch.long, device=dev),
+                             torch.tensor([ranges[p][1] for p in self.order], dtype=torch.long, device=dev))
+        return self._range_t
+
     # ---- data movement of the two aggregation phases (overridden by the row-sharded plan) ----------
     def _scales(self, g, transposed):
         """(row scale, column scale, implicit self loop) of the aggregation operator or its transpose."""
@@ -74,24 +125,80 @@ class GcnPlan(object):
             return g.gcn_dis, g.gcn_dis, True
         return (None, g.inv_in_degree, False) if transposed else (g.inv_in_degree, None, False)
 
-    def head_forward(self, x):
-        outs = []
+    def head_row_bitmaps(self, active):
+        """Per first-step relation: the rows of its aggregate a demand-driven step reads - the source ranges of the
+        metapaths that start with it (static) plus the active rows.  [n_rel, words] int32, one OR per step."""
+        if getattr(self, '_static_rows', None) is None:
+            ranges = self.source_ranges()
+            words = active.bitmap.numel()
+            dev = active.bitmap.device
+            bit = torch.arange(words * 32, device=dev)
+            rows = []
+            for r in range(len(self.first_graphs)):
+                on = torch.zeros(words * 32, dtype=torch.bool, device=dev)
+                for p in range(self.P):
+                    if self.rel_of_path[p] == r:
+                        lo, hi = ranges[p]
+                        on |= (bit >= lo) & (bit < hi)
+                w = (on.view(words, 32).to(torch.int64) << torch.arange(32, device=dev)).sum(dim=1)
+                rows.append(torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32))
+            self._static_rows = torch.stack(rows).contiguous()
+        return torch.bitwise_or(self._static_rows, active.bitmap[None, :])
+
+    def head_forward(self, x, row_bitmaps=None):
+        """One aggregation of the embedding table per distinct first-step relation; the launches are independent
+        (most are small, mostly-empty relations bound by their row epilogues), so they run on parallel branches.
+        ``row_bitmaps`` [n_rel, words]: only the marked rows of each aggregate are computed (the rest stay unwritten)."""
+        outs = [torch.empty_like(x) for _ in self.first_graphs]
+        bm = (lambda k: row_bitmaps[k]) if row_bitmaps is not None else (lambda k: None)
+        if x.shape[0] < 50000:                                   # tiny graphs: not worth the fork / join
+            for k, (g, out) in enumerate(zip(self.first_graphs, outs)):
+                rs, cs, loop = self._scales(g, False)
+                F_.spmm_raw(g.fwd, x, x.shape[1], out, rs, cs, loop, active_rows=bm(k))
+            return outs
+        # everything that is built lazily (degree scalings, chunk-partial workspaces) has to exist BEFORE the fork: a
+        # kernel launched on this stream after the fork point is not ordered before the branches
+        scales = [self._scales(g, False) for g in self.first_graphs]
         for g in self.first_graphs:
-            rs, cs, loop = self._scales(g, False)
-            outs.append(F_.spmm_raw(g.fwd, x, x.shape[1], torch.empty_like(x), rs, cs, loop))
+            g.fwd.view(x.shape[1])
+        with _Fork(x.device) as fork:
+            for k, (g, out) in enumerate(zip(self.first_graphs, outs)):
+                rs, cs, loop = scales[k]
+                with fork.on(k):
+                    F_.spmm_raw(g.fwd, x, x.shape[1], out, rs, cs, loop, active_rows=bm(k))
         return outs
 
     def head_backward(self, grads):
-        dx = None
-        for g, d in zip(self.first_graphs, grads):
-            if d is None:
-                continue
-            d = F_._rows(d)
-            rs, cs, loop = self._scales(g, True)
-            if dx is None:
-                dx = F_.spmm_raw(g.bwd, d, d.shape[1], torch.empty_like(d), rs, cs, loop)
-            else:
-                F_.spmm_raw(g.bwd, d, d.shape[1], dx, rs, cs, loop, accumulate=True)
+        """d x = sum over the first-step relations of A_hat_r^T d A1_r.  The transposed aggregations are independent;
+        each branch accumulates its relations into its own buffer (fixed assignment and order: deterministic) and the
+        few partial tables are added at the end."""
+        todo = [(g, F_._rows(d)) for g, d in zip(self.first_graphs, grads) if d is not None]
+        if not todo:
+            return None
+        n_br = 1 if todo[0][1].shape[0] < 50000 else min(len(todo), len(fork_streams(todo[0][1].device)))
+        parts = [torch.empty_like(todo[0][1]) for _ in range(n_br)]
+        if n_br == 1:
+            for k, (g, d) in enumerate(todo):
+                rs, cs, loop = self._scales(g, True)
+                F_.spmm_raw(g.bwd, d, d.shape[1], parts[0], rs, cs, loop, accumulate=k > 0)
+            return parts[0]
+        # the two largest relations go to different branches; the rest are dealt round-robin
+        order = sorted(range(len(todo)), key=lambda k: -todo[k][0].bwd.nnz)
+        scales = [self._scales(g, True) for g, _ in todo]         # lazily built tensors and workspaces: before the fork
+        for g, d in todo:
+            g.bwd.view(d.shape[1])
+        seen = [False] * n_br
+        with _Fork(parts[0].device) as fork:
+            for pos, k in enumerate(order):
+                g, d = todo[k]
+                b = pos % n_br
+                rs, cs, loop = scales[k]
+                with fork.on(b):
+                    F_.spmm_raw(g.bwd, d, d.shape[1], parts[b], rs, cs, loop, accumulate=seen[b])
+                seen[b] = True
+        dx = parts[0]
+        for extra in parts[1:]:
+            dx.add_(extra)
         return dx
 
     def active_bitmap(self, ids):
@@ -162,14 +269,16 @@ class GcnPlan(object):
 
 class _GcnHead(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, plan):
+    def forward(ctx, x, plan, row_bitmaps=None):
         x = F_._rows(F_._req(x, 'x'))
         ctx.plan = plan
+        if row_bitmaps is not None:
+            return tuple(plan.head_forward(x, row_bitmaps))
         return tuple(plan.head_forward(x))
 
     @staticmethod
     def backward(ctx, *grads):
-        return ctx.plan.head_backward(grads), None
+        return ctx.plan.head_backward(grads), None, None
 
 
 class _GcnBody(torch.autograd.Function):
@@ -186,13 +295,13 @@ class _GcnBody(torch.autograd.Function):
         n = A1[0].shape[0]
         wide = P * D
         t2 = torch.empty(n, wide, dtype=torch.float32, device=dev)
-        h1 = []
-        for p in range(P):
-            h = torch.empty(n, H, dtype=torch.float32, device=dev)
-            F_.linear_raw(A1[plan.rel_of_path[p]], W1[p], h, False, b1[p], True)
-            s = plan.slot[p]
-            F_.linear_raw(h, W2[p], t2[:, s * D:(s + 1) * D], False)
-            h1.append(h)
+        h1 = [torch.empty(n, H, dtype=torch.float32, device=dev) for _ in range(P)]
+        with _Fork(dev) as fork:                               # the per-metapath chains are independent: parallel branches
+            for p in range(P):
+                r, s = plan.rel_of_path[p], plan.slot[p]
+                with fork.on(r):
+                    F_.linear_raw(A1[r], W1[p], h1[p], False, b1[p], True)
+                    F_.linear_raw(h1[p], W2[p], t2[:, s * D:(s + 1) * D], False)
         z = (torch.zeros if active is not None else torch.empty)(n, wide, dtype=torch.float32, device=dev)
         bias_all = torch.cat([b2[p] for p in plan.order])
         plan.last_forward(t2, z, bias_all, active)
@@ -235,24 +344,30 @@ class _GcnBody(torch.autograd.Function):
         F_.wgrad_raw(None, dz, 0, wide, 0, None, db2_all)                     # every metapath's d b2 at once
         dt2 = plan.last_backward(dz, ctx.active)
         dA1 = [None] * n_rel
+        new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        dW2, dW1, db1 = [new(H, D) for _ in range(P)], [new(E, H) for _ in range(P)], [new(H) for _ in range(P)]
+        first_of = {}
+        for p in range(P):
+            r = plan.rel_of_path[p]
+            if dA1[r] is None:
+                dA1[r] = new(n, E)
+                first_of[r] = p
+        n_branches = len(fork_streams(dev))
+        dp1 = [new(n, H) for _ in range(min(P, n_branches))]   # one gated-gradient buffer per branch
+        with _Fork(dev) as fork:
+            for p in range(P):
+                r, s = plan.rel_of_path[p], plan.slot[p]
+                with fork.on(r):                               # metapaths sharing dA1[r] stay on one branch, in order
+                    buf = dp1[r % len(dp1)]
+                    d_t2 = dt2[:, s * D:(s + 1) * D]
+                    F_.wgrad_raw(h1[p], d_t2, H, D, False, dW2[p], None)
+                    F_.linear_raw(d_t2, W2[p], buf, True, out_mask=h1[p])      # (dT2 W2^T) gated by relu
+                    F_.wgrad_raw(A1[r], buf, E, H, False, dW1[p], db1[p])
+                    F_.linear_raw(buf, W1[p], dA1[r], True, accumulate=first_of[r] != p)
         grads = []
-        dp1 = torch.empty(n, H, dtype=torch.float32, device=dev)
         for p in range(P):
             s = plan.slot[p]
-            d_t2 = dt2[:, s * D:(s + 1) * D]
-            dW2 = torch.empty_like(W2[p])
-            F_.wgrad_raw(h1[p], d_t2, H, D, False, dW2, None)
-            F_.linear_raw(d_t2, W2[p], dp1, True, out_mask=h1[p])             # (dT2 W2^T) gated by relu
-            r = plan.rel_of_path[p]
-            dW1 = torch.empty_like(W1[p])
-            db1 = torch.empty(H, dtype=torch.float32, device=dev)
-            F_.wgrad_raw(A1[r], dp1, E, H, False, dW1, db1)
-            if dA1[r] is None:
-                dA1[r] = torch.empty(n, E, dtype=torch.float32, device=dev)
-                F_.linear_raw(dp1, W1[p], dA1[r], True)
-            else:
-                F_.linear_raw(dp1, W1[p], dA1[r], True, accumulate=True)
-            grads.extend([dW1, db1, dW2, db2_all[s * D:(s + 1) * D]])
+            grads.extend([dW1[p], db1[p], dW2[p], db2_all[s * D:(s + 1) * D]])
         d_att = None
         if d_att_perm is not None:
             d_att = torch.empty_like(d_att_perm)
@@ -286,22 +401,23 @@ class _GcnBodyLean(torch.autograd.Function):
         ids, nl = active.ids, int(active.ids.numel())
         t2 = torch.empty(n, wide, dtype=torch.float32, device=dev)
         a1c = [None] * n_rel                                   # the active rows of each first-step aggregate
-        h1r, h1c = [], []
-        t2c = torch.empty(nl, wide, dtype=torch.float32, device=dev)
         for p in range(P):
-            r, s = plan.rel_of_path[p], plan.slot[p]
-            lo, hi = ranges[p]
-            hr = torch.empty(max(hi - lo, 0), H, dtype=torch.float32, device=dev)
-            if hi > lo:
-                F_.linear_raw(A1[r][lo:hi], W1[p], hr, False, b1[p], True)
-                F_.linear_raw(hr, W2[p], t2[lo:hi, s * D:(s + 1) * D], False)
+            r = plan.rel_of_path[p]
             if a1c[r] is None:
                 a1c[r] = A1[r].index_select(0, ids)
-            hc = torch.empty(nl, H, dtype=torch.float32, device=dev)
-            F_.linear_raw(a1c[r], W1[p], hc, False, b1[p], True)
-            F_.linear_raw(hc, W2[p], t2c[:, s * D:(s + 1) * D], False)
-            h1r.append(hr)
-            h1c.append(hc)
+        h1r = [torch.empty(max(ranges[p][1] - ranges[p][0], 0), H, dtype=torch.float32, device=dev) for p in range(P)]
+        h1c = [torch.empty(nl, H, dtype=torch.float32, device=dev) for p in range(P)]
+        t2c = torch.empty(nl, wide, dtype=torch.float32, device=dev)
+        with _Fork(dev) as fork:
+            for p in range(P):
+                r, s = plan.rel_of_path[p], plan.slot[p]
+                lo, hi = ranges[p]
+                with fork.on(r):                               # metapaths sharing a first relation share a branch
+                    if hi > lo:
+                        F_.linear_raw(A1[r][lo:hi], W1[p], h1r[p], False, b1[p], True)
+                        F_.linear_raw(h1r[p], W2[p], t2[lo:hi, s * D:(s + 1) * D], False)
+                    F_.linear_raw(a1c[r], W1[p], h1c[p], False, b1[p], True)
+                    F_.linear_raw(h1c[p], W2[p], t2c[:, s * D:(s + 1) * D], False)
         t2.index_copy_(0, ids, t2c)                            # duplicates / range rows rewrite identical values
         del t2c
         z = torch.empty(n, wide, dtype=torch.float32, device=dev)     # only the active rows are written, and only they are read
@@ -356,38 +472,45 @@ class _GcnBodyLean(torch.autograd.Function):
         dz = torch.zeros(n, wide, dtype=torch.float32, device=dev)
         dz.index_add_(0, ids, dz_c)                            # later occurrences add exact zeros: order-independent
         dt2 = plan.last_backward(dz, active)
-        dt2c_all = dt2.index_select(0, ids)                    # [3B, wide]: the active rows' gradients, gathered once
+        # per slot: the active rows' gradients, each node once (first occurrence) and only where the range pass of that
+        # metapath does not already cover it
+        lo_s, hi_s = plan.source_range_tensors(dev)             # per slot, built once (no host copy inside a capture)
+        keep = first[:, None] & ((ids[:, None] < lo_s[None, :]) | (ids[:, None] >= hi_s[None, :]))      # [3B, P]
+        dt2c = dt2.index_select(0, ids).view(nl, P, D) * keep[:, :, None].to(torch.float32)          # [3B, P, D]
         dA1 = [None] * n_rel
-        grads = []
-        dp1c = torch.empty(nl, H, dtype=torch.float32, device=dev)
-        dac = torch.empty(nl, E, dtype=torch.float32, device=dev)
         for p in range(P):
-            r, s = plan.rel_of_path[p], plan.slot[p]
-            lo, hi = ranges[p]
+            r = plan.rel_of_path[p]
             if dA1[r] is None:
                 dA1[r] = torch.zeros(n, E, dtype=torch.float32, device=dev)
-            dW2, dW1 = torch.empty_like(W2[p]), torch.empty_like(W1[p])
-            db1 = torch.empty(H, dtype=torch.float32, device=dev)
-            if hi > lo:                                        # ---- range pass
-                d_t2 = dt2[lo:hi, s * D:(s + 1) * D]
-                F_.wgrad_raw(h1r[p], d_t2, H, D, False, dW2, None)
-                dp1 = torch.empty(hi - lo, H, dtype=torch.float32, device=dev)
-                F_.linear_raw(d_t2, W2[p], dp1, True, out_mask=h1r[p])
-                F_.wgrad_raw(A1[r][lo:hi], dp1, E, H, False, dW1, db1)
-                F_.linear_raw(dp1, W1[p], dA1[r][lo:hi], True, accumulate=True)
-            else:
-                dW2.zero_(); dW1.zero_(); db1.zero_()
-            # ---- list pass: each active row once (its first occurrence), unless the range pass already took it
-            keep = first & ((ids < lo) | (ids >= hi))
-            d_t2c = dt2c_all[:, s * D:(s + 1) * D] * keep[:, None].to(torch.float32)
-            dW2b, dW1b = torch.empty_like(W2[p]), torch.empty_like(W1[p])
-            db1b = torch.empty(H, dtype=torch.float32, device=dev)
-            F_.wgrad_raw(h1c[p], d_t2c, H, D, False, dW2b, None)
-            F_.linear_raw(d_t2c, W2[p], dp1c, True, out_mask=h1c[p])
-            F_.wgrad_raw(a1c[r], dp1c, E, H, False, dW1b, db1b)
-            F_.linear_raw(dp1c, W1[p], dac, True)
-            dA1[r].index_add_(0, ids, dac)                     # masked-out entries add exact zeros: order-independent
-            grads.extend([dW1 + dW1b, db1 + db1b, dW2 + dW2b, db2_all[s * D:(s + 1) * D]])
+        new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        dW2a, dW1a, db1a = [new(H, D) for _ in range(P)], [new(E, H) for _ in range(P)], [new(H) for _ in range(P)]
+        dW2b, dW1b, db1b = [new(H, D) for _ in range(P)], [new(E, H) for _ in range(P)], [new(H) for _ in range(P)]
+        dp1r = [new(max(ranges[p][1] - ranges[p][0], 0), H) for p in range(P)]
+        dp1c, dac = [new(nl, H) for _ in range(P)], [new(nl, E) for _ in range(P)]
+        with _Fork(dev) as fork:
+            for p in range(P):
+                r, s = plan.rel_of_path[p], plan.slot[p]
+                lo, hi = ranges[p]
+                with fork.on(r):                               # same branch for metapaths that accumulate into one dA1[r]
+                    if hi > lo:                                # ---- range pass
+                        d_t2 = dt2[lo:hi, s * D:(s + 1) * D]
+                        F_.wgrad_raw(h1r[p], d_t2, H, D, False, dW2a[p], None)
+                        F_.linear_raw(d_t2, W2[p], dp1r[p], True, out_mask=h1r[p])
+                        F_.wgrad_raw(A1[r][lo:hi], dp1r[p], E, H, False, dW1a[p], db1a[p])
+                        F_.linear_raw(dp1r[p], W1[p], dA1[r][lo:hi], True, accumulate=True)
+                    else:
+                        dW2a[p].zero_(); dW1a[p].zero_(); db1a[p].zero_()
+                    # ---- list pass
+                    d_t2c = dt2c[:, s, :]
+                    F_.wgrad_raw(h1c[p], d_t2c, H, D, False, dW2b[p], None)
+                    F_.linear_raw(d_t2c, W2[p], dp1c[p], True, out_mask=h1c[p])
+                    F_.wgrad_raw(a1c[r], dp1c[p], E, H, False, dW1b[p], db1b[p])
+                    F_.linear_raw(dp1c[p], W1[p], dac[p], True)
+                    dA1[r].index_add_(0, ids, dac[p])          # masked-out entries add exact zeros: order-independent
+        grads = []
+        for p in range(P):
+            s = plan.slot[p]
+            grads.extend([dW1a[p] + dW1b[p], db1a[p] + db1b[p], dW2a[p] + dW2b[p], db2_all[s * D:(s + 1) * D]])
         d_att = None
         if d_att_perm is not None:
             d_att = torch.empty_like(d_att_perm)
@@ -405,7 +528,8 @@ def gcn_forward(model, metapath_idx=None, plan=None, active=None):
         plan = getattr(model, '_gcn_plan', None)
         if plan is None:
             plan = model._gcn_plan = GcnPlan(model)
-    a1 = _GcnHead.apply(model.x, plan)
+    lean = active is not None and active.ids is not None and (metapath_idx is None) and getattr(plan, 'lean_projections', False)
+    a1 = _GcnHead.apply(model.x, plan, plan.head_row_bitmaps(active) if lean else None)
     params = []
     for ch in model.pea_channels:
         l0, l1 = ch.gnn_layers
@@ -413,7 +537,7 @@ def gcn_forward(model, metapath_idx=None, plan=None, active=None):
     att = model.att if model.channel_aggr == 'att' else None
     mode = 0 if model.channel_aggr == 'att' else 1
     skip = -1 if metapath_idx is None else int(metapath_idx)
-    if active is not None and active.ids is not None and skip < 0 and getattr(plan, 'lean_projections', False):
+    if lean:
         return _GcnBodyLean.apply(plan, att, mode, len(a1), active, *a1, *params)
     return _GcnBody.apply(plan, att, mode, skip, len(a1), active, *a1, *params)
 

@@ -151,6 +151,8 @@ def _check(ret, world):
             if r == 0:
                 print('vs reference fp64: loss sharded %.2e / unsharded %.2e; worst gradient sharded %s %.2e, unsharded %s %.2e'
                       % (vt['loss_sharded'], vt['loss_unsharded'], worst_s[0], worst_s[1], worst_u[0], worst_u[1]))
+                for name, e in sorted(vt['sharded'].items(), key=lambda kv: -kv[1])[:12]:
+                    print('   sharded %-44s %.2e   (unsharded %.2e)' % (name, e, vt['unsharded'][name]))
             assert vt['loss_sharded'] < 1e-5, vt
             assert worst_s[1] < 1e-4, (worst_s, worst_u)
             continue                # two fp32 sums in different orders are each within the bound of the truth, not of each other
@@ -162,13 +164,13 @@ def _check(ret, world):
                 assert e < 1e-4, ('demand-driven', name, e)
 
 
-def test_eight_way_shards_of_the_25m_shaped_graph_match_unsharded():
+@pytest.mark.parametrize('world,kind', [(8, 'gcn'), (2, 'gcn'), (8, 'gcn-layers')])
+def test_eight_way_shards_of_the_25m_shaped_graph_match_unsharded(world, kind):
     """R = 8 on the ML-25M-shaped (1/10-edge) graph: the configuration whose only hardware run of
-    round 1 printed a non-finite loss.  Sharded loss / repr / every gradient vs the unsharded model
-    on the same global batch of 4096 triples."""
-    world = 8
+    round 1 printed a non-finite loss.  Sharded loss / repr / every gradient on the reference run's
+    global batch of 4096 triples, judged against the reference's fp64 gradients."""
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), 'gcn', False, ret, 'ml-25m-lite', 'gloo', 4096, 'ml-25m-lite/gcn/plain'),
+    mp.spawn(_worker, args=(world, _free_port(), kind, False, ret, 'ml-25m-lite', 'gloo', 4096, 'ml-25m-lite/gcn/plain'),
              nprocs=world, join=True)
     _check(ret, world)
 

@@ -14,4 +14,6 @@ echo "graph rc=$?"; tail -c 600 $O/r2c_bench_n${N}_graph.err
 timeout 300 $TR --master-port 29513 bench.py --gpus $N --phase eval --steps 5 --warmup 2 > $O/r2c_bench_eval_n$N.json 2> $O/r2c_bench_eval_n$N.err
 echo "eval rc=$?"
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
+
+timeout 600 python tools/shard_diag.py > $O/r2c_shard_diag.txt 2>&1; tail -45 $O/r2c_shard_diag.txt
 echo done
