@@ -434,8 +434,9 @@ def product_train(c):
     dist, _lib, F_, barrier = c['dist'], c['lib'], c['F_'], c['barrier']
     from graph_recsys_benchmark_b200.graphed import GraphedTrainStep
     params = [p for p in model.parameters()]
-    # one GPU: the step is replayed as one CUDA graph.  Multi-GPU: eager launches unless PEAGNN_BENCH_GRAPH_MULTI
-    use_graph = not args.no_cuda_graph and (world == 1 or bool(os.environ.get('PEAGNN_BENCH_GRAPH_MULTI')))
+    # the step - NCCL collectives included - is replayed as one CUDA graph (graphed.py captures in 'thread_local' mode so
+    # that NCCL's watchdog thread cannot invalidate the capture); PEAGNN_BENCH_EAGER_MULTI=1 keeps N > 1 on eager launches
+    use_graph = not args.no_cuda_graph and (world == 1 or not os.environ.get('PEAGNN_BENCH_EAGER_MULTI'))
     opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-3, fused=True, capturable=use_graph)
     model.train()
     K, W, B = args.steps, args.warmup, args.batch
