@@ -43,6 +43,9 @@ SIGNATURES = {
     'peagnn_partial_floats': (_SZ, [_I32, _I32, _I32]),
     'peagnn_spmm': (_INT, [_G, _P, _I64, _I32, _P, _I64, _P, _P, _INT, _P, _INT, _INT, _P]),
     'peagnn_spmm_filtered': (_INT, [_G, _P, _I64, _I32, _P, _I64, _P, _P, _INT, _P, _INT, _INT, _P, _P, _P]),
+    'peagnn_spmm_proj': (_INT, [_G, _P, _I64, _P, _I64, _P, _P, _INT, _P, _I32, _P, _P, _P, _P, _P, _P, _I64, _INT, _P]),
+    'peagnn_to_bf16': (_INT, [_P, _I64, _I64, _I32, _P, _I64, _P]),
+    'peagnn_spmm_bf16': (_INT, [_G, _P, _I64, _I32, _P, _I64, _P, _P, _INT, _P, _INT, _INT, _P, _P, _P]),
     'peagnn_mark_rows': (_INT, [_P, _I64, _I32, _I32, _P, _P]),
     'peagnn_gat_rowmax': (_INT, [_G, _P, _P, _I32, _F, _P, _P]),
     'peagnn_gat_aggregate': (_INT, [_G, _P, _I64, _I32, _I32, _P, _P, _F, _P, _P, _P, _I64, _P, _INT, _P]),

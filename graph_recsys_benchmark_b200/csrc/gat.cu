@@ -80,20 +80,21 @@ struct GatAggOp {
     e.w2 = 0.f;
     return e;
   }
+  // no per-lane predicate in the gather loop (see SpmmOp::apply): lanes beyond the row width re-read its last chunk and
+  // their sums are never stored; `valid` is the literal true on the full-batch path
   __device__ __forceinline__ void apply(float* acc, int, int c, float w, float, int gl, bool valid) const {
+    if (!valid) { w = 0.f; c = 0; }      // idle slots: row 0 always exists in the gathered table, the view's safe row may not
     const float* xr = H + row_off(c, (unsigned)ldh) + h_ * feat;
 #pragma unroll
     for (int ch = 0; ch < CPL; ++ch) {
-      const int idx = gl + ch * G;
-      if (valid && idx < f4) {
-        const float4 v = ldg4(xr + 4 * idx);
-        acc[4 * ch + 0] = fmaf(w, v.x, acc[4 * ch + 0]);
-        acc[4 * ch + 1] = fmaf(w, v.y, acc[4 * ch + 1]);
-        acc[4 * ch + 2] = fmaf(w, v.z, acc[4 * ch + 2]);
-        acc[4 * ch + 3] = fmaf(w, v.w, acc[4 * ch + 3]);
-      }
+      float4 v = ldg4(xr + 4 * min(gl + ch * G, f4 - 1));
+      if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[4 * ch + 0] = fmaf(w, v.x, acc[4 * ch + 0]);
+      acc[4 * ch + 1] = fmaf(w, v.y, acc[4 * ch + 1]);
+      acc[4 * ch + 2] = fmaf(w, v.z, acc[4 * ch + 2]);
+      acc[4 * ch + 3] = fmaf(w, v.w, acc[4 * ch + 3]);
     }
-    if (valid) acc[4 * CPL] += w;
+    acc[4 * CPL] += w;
   }
   __device__ __forceinline__ void finish(float* acc, int i, int h, int gl, bool writer) const {
     if (!writer) return;
@@ -268,19 +269,18 @@ struct GatBwdSrcOp {
     return r;
   }
   __device__ __forceinline__ void apply(float* acc, int, int c, float w, float w2, int gl, bool valid) const {
+    if (!valid) { w = 0.f; w2 = 0.f; c = 0; }
     const float* xr = dout + row_off(c, (unsigned)ldd) + h_ * feat;
 #pragma unroll
     for (int ch = 0; ch < CPL; ++ch) {
-      const int idx = gl + ch * G;
-      if (valid && idx < f4) {
-        const float4 v = ldg4(xr + 4 * idx);
-        acc[4 * ch + 0] = fmaf(w, v.x, acc[4 * ch + 0]);
-        acc[4 * ch + 1] = fmaf(w, v.y, acc[4 * ch + 1]);
-        acc[4 * ch + 2] = fmaf(w, v.z, acc[4 * ch + 2]);
-        acc[4 * ch + 3] = fmaf(w, v.w, acc[4 * ch + 3]);
-      }
+      float4 v = ldg4(xr + 4 * min(gl + ch * G, f4 - 1));
+      if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[4 * ch + 0] = fmaf(w, v.x, acc[4 * ch + 0]);
+      acc[4 * ch + 1] = fmaf(w, v.y, acc[4 * ch + 1]);
+      acc[4 * ch + 2] = fmaf(w, v.z, acc[4 * ch + 2]);
+      acc[4 * ch + 3] = fmaf(w, v.w, acc[4 * ch + 3]);
     }
-    if (valid) acc[4 * CPL] += w2;
+    acc[4 * CPL] += w2;
   }
   __device__ __forceinline__ void finish(float* acc, int i, int h, int gl, bool writer) const {
     if (!writer) return;

@@ -101,9 +101,46 @@ class ShardedRelation(object):
         self.scale_local = torch.where(valid, scale[own.clamp(min=0)], torch.zeros_like(own, dtype=scale.dtype)).contiguous()
         self.src, self.dst_local = shard_coo(edge_index, plan, explicit_self_loops=loops, drop_self_loops=loops)
         self.explicit_self_loops = loops
+        self.n_loops = int(valid.sum().item()) if loops else 0          # the explicit self loops are the LAST n_loops edges
+        # node-id range holding every source of the relation (ids are contiguous by type upstream): what a step that
+        # gathers through this relation actually reads of an exchanged table
+        real = src[nl]
+        self.src_lo = int(real.min().item()) if real.numel() else 0
+        self.src_hi = int(real.max().item()) + 1 if real.numel() else 0
         self._fwd, self._bwd, self._perm = {}, {}, {}
+        self._src_layout = None
+
+    def src_layout(self):
+        """Compact exchange layout: every rank contributes only its rows inside the source range
+        [src_lo, src_hi) - a contiguous local slice [start_q, start_q + cmax) - and the table a shard gathers from is
+        [R * cmax exchanged rows | this rank's own rows (the self-loop targets, no exchange needed)]."""
+        if self._src_layout is None:
+            R, rpr, n = self.plan.world, self.plan.rows_per_rank, self.plan.num_nodes
+            lo_q = [max(0, -((q - self.src_lo) // R)) for q in range(R)]
+            hi_q = [min(rpr, max(0, -((q - self.src_hi) // R))) for q in range(R)]
+            cmax = max(1, max(h - l for l, h in zip(lo_q, hi_q)))
+            start = [max(0, min(l, rpr - cmax)) for l in lo_q]
+            dev = self.src.device
+            start_t = torch.tensor(start, dtype=torch.long, device=dev)
+            n_real = self.src.numel() - self.n_loops
+            s_real, loops_local = self.src[:n_real], self.dst_local[n_real:]
+            owner = s_real % R
+            pos = owner * cmax + (s_real // R - start_t[owner])
+            assert n_real == 0 or (int(pos.min()) >= 0 and bool(((s_real // R - start_t[owner]) < cmax).all()))
+            cols = torch.cat([pos, R * cmax + loops_local])
+            # column scale of every table row: exchanged part by the node it holds (0 for slots beyond N), then the own rows
+            q = torch.arange(R, device=dev).repeat_interleave(cmax)
+            j = torch.arange(cmax, device=dev).repeat(R)
+            gid = (start_t[q] + j) * R + q
+            ok = gid < n
+            cs_x = torch.where(ok, self.scale_orig[gid.clamp(max=n - 1)], torch.zeros_like(gid, dtype=self.scale_orig.dtype))
+            self._src_layout = dict(cmax=cmax, start=start, rows=R * cmax + rpr, cols=cols,
+                                    scale=torch.cat([cs_x, self.scale_local]).contiguous())
+        return self._src_layout
 
     def _cols(self, layout):
+        if layout == 'src':
+            return self.src_layout()['cols']
         return self.src if layout == 'orig' else self.plan.to_rank_major(self.src)
 
     def fwd(self, layout):
@@ -115,7 +152,8 @@ class ShardedRelation(object):
 
     def bwd(self, layout):
         if layout not in self._bwd:
-            rows = self.plan.num_nodes if layout == 'orig' else self.plan.padded
+            rows = self.plan.num_nodes if layout == 'orig' else \
+                (self.src_layout()['rows'] if layout == 'src' else self.plan.padded)
             csr = build_csr(self._cols(layout), self.dst_local, rows, False)
             csr.explicit_self_loops = self.explicit_self_loops
             self._bwd[layout] = csr
@@ -131,6 +169,8 @@ class ShardedRelation(object):
         return self._perm[layout]
 
     def table_scale(self, layout):
+        if layout == 'src':
+            return self.src_layout()['scale']
         return self.scale_orig if layout == 'orig' else self.scale_rm
 
 
@@ -545,6 +585,7 @@ class ShardedGcnPlan(object):
         first = model.pea_channels[0].gnn_layers
         self.emb, self.hidden, self.repr = first[0].in_channels, first[0].out_channels, first[1].out_channels
         self._table = self._dtab = None
+        self._xbuf = {}
 
     def head_forward(self, x):
         from .engine import _Fork
@@ -571,27 +612,65 @@ class ShardedGcnPlan(object):
                 F_.spmm_raw(rel.bwd('orig'), d, d.shape[1], dx, rel.scale_orig, rel.scale_local, False, accumulate=True)
         return dx
 
+    compact_exchange = True      # exchange only each last-step relation's source-type rows (False: the whole [N, P*repr] table)
+
+    def _exchange_buffers(self, k, rows, width, dev):
+        key = (k, rows, width)
+        if key not in self._xbuf:
+            self._xbuf[key] = (torch.empty(rows, width, dtype=torch.float32, device=dev),
+                               torch.empty(rows, width, dtype=torch.float32, device=dev))
+        return self._xbuf[key]
+
     def last_forward(self, t2, z, bias_all, active=None):
+        rows_bm = active.bitmap if active is not None else None
+        D, start = self.repr, 0
+        if self.compact_exchange:
+            R, rpr, group = self.sp.plan.world, self.sp.plan.rows_per_rank, self.sp.group
+            for k, (rel, members) in enumerate(self.groups):
+                width = len(members) * D
+                lay = rel.src_layout()
+                cmax, s0 = lay['cmax'], lay['start'][self.sp.plan.rank]
+                table, _ = self._exchange_buffers(k, lay['rows'], width, t2.device)
+                raw_all_gather(t2[s0:s0 + cmax, start:start + width], group, out=table[:R * cmax])   # source-range rows only
+                table[R * cmax:].copy_(t2[:, start:start + width])                                   # own rows: self loops
+                F_.spmm_raw(rel.fwd('src'), table, width, z[:, start:start + width], rel.scale_local, lay['scale'], False,
+                            bias_all[start:start + width], active_rows=rows_bm)
+                start += width
+            return
         if self._table is None or self._table.shape != (self.sp.plan.padded, t2.shape[1]):
             self._table = torch.empty(self.sp.plan.padded, t2.shape[1], dtype=torch.float32, device=t2.device)
         table = raw_all_gather(t2, self.sp.group, out=self._table)     # the step's only all-gather
-        D, start = self.repr, 0
         for rel, members in self.groups:
             width = len(members) * D
             F_.spmm_raw(rel.fwd('rm'), table[:, start:start + width], width, z[:, start:start + width],
-                        rel.scale_local, rel.scale_rm, False, bias_all[start:start + width],
-                        active_rows=active.bitmap if active is not None else None)
+                        rel.scale_local, rel.scale_rm, False, bias_all[start:start + width], active_rows=rows_bm)
             start += width
 
     def last_backward(self, dz, active=None):
+        cols_bm = active.bitmap if active is not None else None
+        D, start = self.repr, 0
+        if self.compact_exchange:
+            R, rpr, group = self.sp.plan.world, self.sp.plan.rows_per_rank, self.sp.group
+            dt2 = torch.empty_like(dz)
+            for k, (rel, members) in enumerate(self.groups):
+                width = len(members) * D
+                lay = rel.src_layout()
+                cmax, s0 = lay['cmax'], lay['start'][self.sp.plan.rank]
+                _, dtab = self._exchange_buffers(k, lay['rows'], width, dz.device)
+                F_.spmm_raw(rel.bwd('src'), dz[:, start:start + width], width, dtab, lay['scale'], rel.scale_local, False,
+                            active_cols=cols_bm)
+                dt2[:, start:start + width].copy_(dtab[R * cmax:])                       # the self-loop part stays local
+                mine = raw_reduce_scatter(dtab[:R * cmax], group)                        # [cmax, width] summed over ranks
+                dt2[s0:s0 + cmax, start:start + width] += mine
+                start += width
+            return dt2
         if self._dtab is None or self._dtab.shape != (self.sp.plan.padded, dz.shape[1]):
             self._dtab = torch.empty(self.sp.plan.padded, dz.shape[1], dtype=torch.float32, device=dz.device)
         dtab = self._dtab
-        D, start = self.repr, 0
         for rel, members in self.groups:
             width = len(members) * D
             F_.spmm_raw(rel.bwd('rm'), dz[:, start:start + width], width, dtab[:, start:start + width],
-                        rel.scale_rm, rel.scale_local, False, active_cols=active.bitmap if active is not None else None)
+                        rel.scale_rm, rel.scale_local, False, active_cols=cols_bm)
             start += width
         return raw_reduce_scatter(dtab, self.sp.group)                 # ... and its only reduce-scatter
 

@@ -75,12 +75,16 @@ class ActiveSet(object):
 
     def __init__(self, bitmap, ids=None, first=None):
         self.bitmap, self.ids, self.first = bitmap, ids, first
+        self.h1_full = None      # per metapath [N, hidden]: first-layer activations written by the head's fused epilogue
 
 
 class GcnPlan(object):
     """Static schedule of a model: which relation feeds which metapath, and the column layout.
     ``kind`` 'gcn' (normalised sum with self loops) or 'sage' (mean over in-edges, no self loops)."""
     lean_projections = True      # demand-driven loss(): projections on the last step's source range + the active rows
+    head_params = None           # set per call by gcn_forward: [(W1_p, b1_p)] when the first projections are fused into the head
+    head_h1 = None               # ... and the activations that epilogue wrote, per metapath [N, hidden]
+    gather_bf16 = False          # opt-in (model.gather_dtype = 'bf16'): first-step tables are gathered from a bf16 copy
 
     def __init__(self, model, kind='gcn'):
         n = model.x.shape[0]
@@ -151,10 +155,38 @@ class GcnPlan(object):
         ``row_bitmaps`` [n_rel, words]: only the marked rows of each aggregate are computed (the rest stay unwritten)."""
         outs = [torch.empty_like(x) for _ in self.first_graphs]
         bm = (lambda k: row_bitmaps[k]) if row_bitmaps is not None else (lambda k: None)
+        bf16 = self.gather_bf16 and x.shape[1] == 64
+        # north_star (2): the first projection of every metapath rides in the epilogue of its relation's aggregation
+        # (peagnn_spmm_proj) - demand-driven GCN steps with 64 -> 64 first layers; the activations land in head_h1
+        fused = self.head_params is not None and not bf16 and x.shape[1] == 64 and self.hidden == 64 and self.kind == 'gcn'
+        self.head_h1 = None
+        if fused:
+            by_rel = [[p for p in range(self.P) if self.rel_of_path[p] == k] for k in range(len(self.first_graphs))]
+            fused = all(1 <= len(ps) <= 2 for ps in by_rel)
+        if fused:
+            self.head_h1 = [torch.empty(x.shape[0], self.hidden, dtype=torch.float32, device=x.device) for _ in range(self.P)]
+            proj = [[(self.head_params[p][0], self.head_params[p][1], self.head_h1[p]) for p in ps] for ps in by_rel]
+
+        if fused:
+            scales = [self._scales(g, False) for g in self.first_graphs]
+            for g in self.first_graphs:
+                g.fwd.view(64)
+            parallel = x.shape[0] >= 50000
+            with _Fork(x.device) as fork:
+                for k, (g, out) in enumerate(zip(self.first_graphs, outs)):
+                    rs, cs, loop = scales[k]
+                    if parallel:
+                        with fork.on(k):
+                            F_.spmm_proj_raw(g.fwd, x, out, rs, cs, loop, proj[k], True, bm(k))
+                    else:
+                        F_.spmm_proj_raw(g.fwd, x, out, rs, cs, loop, proj[k], True, bm(k))
+            return outs
+        table = F_.to_bf16(x) if bf16 else x                     # opt-in: the gathered copy of the embedding table in bf16
+        agg = F_.spmm_bf16_raw if bf16 else F_.spmm_raw
         if x.shape[0] < 50000:                                   # tiny graphs: not worth the fork / join
             for k, (g, out) in enumerate(zip(self.first_graphs, outs)):
                 rs, cs, loop = self._scales(g, False)
-                F_.spmm_raw(g.fwd, x, x.shape[1], out, rs, cs, loop, active_rows=bm(k))
+                agg(g.fwd, table, x.shape[1], out, rs, cs, loop, active_rows=bm(k))
             return outs
         # everything that is built lazily (degree scalings, chunk-partial workspaces) has to exist BEFORE the fork: a
         # kernel launched on this stream after the fork point is not ordered before the branches
@@ -165,7 +197,7 @@ class GcnPlan(object):
             for k, (g, out) in enumerate(zip(self.first_graphs, outs)):
                 rs, cs, loop = scales[k]
                 with fork.on(k):
-                    F_.spmm_raw(g.fwd, x, x.shape[1], out, rs, cs, loop, active_rows=bm(k))
+                    agg(g.fwd, table, x.shape[1], out, rs, cs, loop, active_rows=bm(k))
         return outs
 
     def head_backward(self, grads):
@@ -177,10 +209,14 @@ class GcnPlan(object):
             return None
         n_br = 1 if todo[0][1].shape[0] < 50000 else min(len(todo), len(fork_streams(todo[0][1].device)))
         parts = [torch.empty_like(todo[0][1]) for _ in range(n_br)]
+        # opt-in bf16 gathers: worth the conversion pass only where the gather dominates (the relations with many edges)
+        use_bf16 = [self.gather_bf16 and d.shape[1] == 64 and g.bwd.nnz >= 8 * d.shape[0] for g, d in todo]
+        tables = [F_.to_bf16(d) if b else d for (g, d), b in zip(todo, use_bf16)]
+        aggs = [F_.spmm_bf16_raw if b else F_.spmm_raw for b in use_bf16]
         if n_br == 1:
             for k, (g, d) in enumerate(todo):
                 rs, cs, loop = self._scales(g, True)
-                F_.spmm_raw(g.bwd, d, d.shape[1], parts[0], rs, cs, loop, accumulate=k > 0)
+                aggs[k](g.bwd, tables[k], d.shape[1], parts[0], rs, cs, loop, accumulate=k > 0)
             return parts[0]
         # the two largest relations go to different branches; the rest are dealt round-robin
         order = sorted(range(len(todo)), key=lambda k: -todo[k][0].bwd.nnz)
@@ -194,7 +230,7 @@ class GcnPlan(object):
                 b = pos % n_br
                 rs, cs, loop = scales[k]
                 with fork.on(b):
-                    F_.spmm_raw(g.bwd, d, d.shape[1], parts[b], rs, cs, loop, accumulate=seen[b])
+                    aggs[k](g.bwd, tables[k], d.shape[1], parts[b], rs, cs, loop, accumulate=seen[b])
                 seen[b] = True
         dx = parts[0]
         for extra in parts[1:]:
@@ -405,8 +441,13 @@ class _GcnBodyLean(torch.autograd.Function):
             r = plan.rel_of_path[p]
             if a1c[r] is None:
                 a1c[r] = A1[r].index_select(0, ids)
-        h1r = [torch.empty(max(ranges[p][1] - ranges[p][0], 0), H, dtype=torch.float32, device=dev) for p in range(P)]
-        h1c = [torch.empty(nl, H, dtype=torch.float32, device=dev) for p in range(P)]
+        pre = active.h1_full                                   # first-layer activations from the head's fused epilogue
+        if pre is not None:
+            h1r = [pre[p][ranges[p][0]:ranges[p][1]] for p in range(P)]
+            h1c = [pre[p].index_select(0, ids) for p in range(P)]
+        else:
+            h1r = [torch.empty(max(ranges[p][1] - ranges[p][0], 0), H, dtype=torch.float32, device=dev) for p in range(P)]
+            h1c = [torch.empty(nl, H, dtype=torch.float32, device=dev) for p in range(P)]
         t2c = torch.empty(nl, wide, dtype=torch.float32, device=dev)
         with _Fork(dev) as fork:
             for p in range(P):
@@ -414,9 +455,11 @@ class _GcnBodyLean(torch.autograd.Function):
                 lo, hi = ranges[p]
                 with fork.on(r):                               # metapaths sharing a first relation share a branch
                     if hi > lo:
-                        F_.linear_raw(A1[r][lo:hi], W1[p], h1r[p], False, b1[p], True)
+                        if pre is None:
+                            F_.linear_raw(A1[r][lo:hi], W1[p], h1r[p], False, b1[p], True)
                         F_.linear_raw(h1r[p], W2[p], t2[lo:hi, s * D:(s + 1) * D], False)
-                    F_.linear_raw(a1c[r], W1[p], h1c[p], False, b1[p], True)
+                    if pre is None:
+                        F_.linear_raw(a1c[r], W1[p], h1c[p], False, b1[p], True)
                     F_.linear_raw(h1c[p], W2[p], t2c[:, s * D:(s + 1) * D], False)
         t2.index_copy_(0, ids, t2c)                            # duplicates / range rows rewrite identical values
         del t2c
@@ -528,16 +571,22 @@ def gcn_forward(model, metapath_idx=None, plan=None, active=None):
         plan = getattr(model, '_gcn_plan', None)
         if plan is None:
             plan = model._gcn_plan = GcnPlan(model)
+    plan.gather_bf16 = getattr(model, 'gather_dtype', 'fp32') == 'bf16'
     lean = active is not None and active.ids is not None and (metapath_idx is None) and getattr(plan, 'lean_projections', False)
-    a1 = _GcnHead.apply(model.x, plan, plan.head_row_bitmaps(active) if lean else None)
     params = []
     for ch in model.pea_channels:
         l0, l1 = ch.gnn_layers
         params.extend([l0.weight, l0.bias, l1.weight, l1.bias])
+    plan.head_params = [(params[4 * p].detach(), params[4 * p + 1].detach()) for p in range(plan.P)] \
+        if (lean and getattr(model, 'fuse_first_projection', True)) else None
+    a1 = _GcnHead.apply(model.x, plan, plan.head_row_bitmaps(active) if lean else None)
+    h1_full = plan.head_h1 if lean else None
+    plan.head_params = None
     att = model.att if model.channel_aggr == 'att' else None
     mode = 0 if model.channel_aggr == 'att' else 1
     skip = -1 if metapath_idx is None else int(metapath_idx)
     if lean:
+        active.h1_full = h1_full
         return _GcnBodyLean.apply(plan, att, mode, len(a1), active, *a1, *params)
     return _GcnBody.apply(plan, att, mode, skip, len(a1), active, *a1, *params)
 

@@ -73,6 +73,53 @@ def spmm_raw(csr, X, feat, out, rs=None, cs=None, self_loop=False, bias=None, re
     return out
 
 
+def spmm_proj_raw(csr, X, out, rs, cs, self_loop, projections, relu=True, active_rows=None):
+    """Aggregation of a 64-wide table with up to two first projections fused into its epilogue.
+    ``projections``: [(W [64, 64] (in, out), b or None, H out tensor [N, 64])]."""
+    view = csr.view(64)
+    tag, nbytes = None, 0
+    if _lib.profile is not None:
+        filtered = active_rows is not None
+        tag = 'spmm%s_proj%d_f64_e%d_n%d_h%d' % ('_filtered' if filtered else '', len(projections), csr.nnz, view.nrows, view.n_heavy)
+        nbytes = (csr.nnz * 4 + view.nrows * 256) if filtered else \
+            spmm_algorithmic_bytes(csr.nnz, view.nrows, 64, rs is not None, cs is not None, self_loop) + len(projections) * view.nrows * 256
+    (W0, b0, H0) = projections[0]
+    (W1, b1, H1) = projections[1] if len(projections) > 1 else (None, None, None)
+    with _on(X.device):
+        _lib.call('peagnn_spmm_proj', C.byref(view), _ptr(X), X.stride(0), _ptr(out), out.stride(0), _ptr(rs), _ptr(cs),
+                  int(self_loop), _ptr(active_rows), len(projections), _ptr(W0), _ptr(b0), _ptr(H0), _ptr(W1), _ptr(b1), _ptr(H1),
+                  H0.stride(0), int(relu), _stream(), tag=tag, nbytes=nbytes)
+    return out
+
+
+def to_bf16(X):
+    """bf16 copy (int16 bit patterns, same shape) of an fp32 table whose width is a multiple of 8."""
+    X = _rows(_req(X, 'table'))
+    out = torch.empty(X.shape[0], X.shape[1], dtype=torch.int16, device=X.device)
+    with _on(X.device):
+        _lib.call('peagnn_to_bf16', _ptr(X), X.stride(0), X.shape[0], X.shape[1], _ptr(out), out.stride(0), _stream())
+    return out
+
+
+def spmm_bf16_raw(csr, Xb, feat, out, rs=None, cs=None, self_loop=False, bias=None, relu=False, accumulate=False,
+                  active_rows=None, active_cols=None):
+    """spmm_raw gathering a bf16 table (``to_bf16``); fp32 accumulation and output."""
+    view = csr.view(feat)
+    tag, nbytes = None, 0
+    if _lib.profile is not None:
+        filtered = active_rows is not None or active_cols is not None
+        tag = 'spmm%s_bf16_f%d_e%d_n%d_h%d' % ('_filtered' if filtered else '', feat, csr.nnz, view.nrows, view.n_heavy)
+        # gathered rows are 2 bytes per element, the own row (self loop) too, the output row 4
+        per_edge = 4 + (4 if cs is not None else 0) + 2 * feat
+        per_row = (2 * feat if self_loop else 0) + (4 if rs is not None else 0) + 4 * feat + (4 * feat if accumulate else 0)
+        nbytes = (csr.nnz * 4 + view.nrows * 4 * feat) if filtered else csr.nnz * per_edge + view.nrows * per_row + (view.nrows + 1) * 4
+    with _on(out.device):
+        _lib.call('peagnn_spmm_bf16', C.byref(view), _ptr(Xb), Xb.stride(0), feat, _ptr(out), out.stride(0), _ptr(rs), _ptr(cs),
+                  int(self_loop), _ptr(bias), int(relu), int(accumulate), _ptr(active_rows), _ptr(active_cols), _stream(),
+                  tag=tag, nbytes=nbytes)
+    return out
+
+
 def mark_rows(ids, n_bits, mod=0, rem=0):
     """Bitmap (int32 words) with bit ``id`` set for every id in ``ids`` (int64, any shape); with ``mod`` > 1 only ids
     with ``id % mod == rem`` count and their bit index is ``id // mod`` (the local row id under cyclic sharding)."""

@@ -153,6 +153,8 @@ class PEABaseRecsysModel(GraphRecsysModel):
     batch_last_step = True     # one aggregation per distinct last-step relation (columns concatenated)
     fused_engine = True        # engine.py: head / body autograd nodes instead of one node per kernel
     demand_driven_loss = False  # loss() computes only the representation rows its batch reads (BaseSolver turns it on)
+    gather_dtype = 'fp32'       # 'bf16' (opt-in, PEAGCN engine): the first-step aggregations gather a bf16 copy of their
+                                # table - fp32 accumulation and outputs, results within the tolerance of tests/test_gpu_bf16.py
 
     def _engine_kind(self):
         ok = getattr(self, '_engine_ok', None)

@@ -126,6 +126,27 @@ int peagnn_spmm_filtered(const peagnn_csr_t* g, const float* X, int64_t ldx, int
                          float* out, int64_t ldo, const float* rs, const float* cs, int self_loop,
                          const float* bias, int relu, int accumulate, const uint32_t* active_rows,
                          const uint32_t* active_cols, peagnn_stream_t stream);
+/* north_star (2): GCN aggregation of a 64-wide table with the channel's first projection fused into the epilogue
+ * (models/base.py:137-139 with models/peagcn.py:16-21: relu(GCNConv(x)) = relu((A_hat x) W + b)):
+ *   out[i,:] = rs[i] * ( sum_e cs[col_e] X[col_e,:] + self_loop * cs[i] X[i,:] )            (the aggregate, still written)
+ *   H_q[i,:] = act( out[i,:] @ W_q + b_q ),  q < n_proj <= 2,  W_q [64, 64] row-major (GCNConv.weight), b_q may be NULL
+ * while the aggregated row is in registers; fp32 FMA.  active_rows as in peagnn_spmm_filtered (NULL = every row). */
+int peagnn_spmm_proj(const peagnn_csr_t* g, const float* X, int64_t ldx, float* out, int64_t ldo, const float* rs,
+                     const float* cs, int self_loop, const uint32_t* active_rows, int32_t n_proj,
+                     const float* W0, const float* b0, float* H0, const float* W1, const float* b1, float* H1,
+                     int64_t ldh, int relu, peagnn_stream_t stream);
+
+/* Opt-in bf16 storage of a GATHERED table (north_star: "64-dim bf16/fp32 node rows"): peagnn_to_bf16 rounds an fp32
+ * table to bf16 (nearest even; uint16 bit patterns, ldo in elements, multiple of 8), peagnn_spmm_bf16 is peagnn_spmm /
+ * peagnn_spmm_filtered reading that table - 16-byte loads of 8 elements, four edges per warp instruction, half the L2
+ * bytes; scales, accumulation, bias and the output are fp32.  feat = 64 only (the first-step tables).  The result
+ * differs from the fp32 path by the rounding of the gathered values only (2^-9 relative per element; stated
+ * tolerances in tests/test_gpu_bf16.py). */
+int peagnn_to_bf16(const float* X, int64_t ldx, int64_t n, int32_t feat, uint16_t* out, int64_t ldo,
+                   peagnn_stream_t stream);
+int peagnn_spmm_bf16(const peagnn_csr_t* g, const uint16_t* Xb, int64_t ldx, int32_t feat, float* out, int64_t ldo,
+                     const float* rs, const float* cs, int self_loop, const float* bias, int relu, int accumulate,
+                     const uint32_t* active_rows, const uint32_t* active_cols, peagnn_stream_t stream);
 /* bitmap[(id / mod) >> 5] |= 1 << ((id / mod) & 31) for every id with id % mod == rem (mod <= 1: every id,
  * bit index = id).  bitmap is pre-zeroed by the caller; ids int64 [n].  mod / rem select and renumber the
  * rows a rank owns under cyclic row sharding. */

@@ -433,3 +433,38 @@ def test_bpr_and_entity_gradients_are_bit_reproducible():
     loss = F_.bpr_loss(big, w1, torch.zeros(D, device=DEV), torch.ones(1, D, device=DEV), torch.zeros(1, device=DEV),
                        torch.tensor([[0, 1, 2]], device=DEV))
     assert torch.isfinite(loss) and abs(loss.item() - 640.0) < 1e-3        # softplus(640) = 640
+
+
+@pytest.mark.parametrize('gname', ['small', 'heavy', 'bipartite', 'isolated'])
+@pytest.mark.parametrize('n_proj', [1, 2])
+def test_aggregation_with_the_first_projection_in_its_epilogue(gname, n_proj):
+    """peagnn_spmm_proj (north_star (2)): relu((A_hat X) W + b) computed while the aggregated row is in registers
+    equals the two-launch form, on every row path of the traversal engine (light, heavy / chunked, edge-less) and with
+    the row filter."""
+    from graph_recsys_benchmark_b200 import functional as F_
+    spec = dict(GRAPHS[gname])
+    n = spec.pop('n')
+    ei = random_edge_index(n, spec.pop('e'), 9, self_loops=spec.pop('loops'), multi=spec.pop('multi'), **spec)
+    g = _graph(ei, n)
+    torch.manual_seed(2)
+    X = torch.randn(n, 64, device=DEV)
+    dis = g.gcn_dis
+    Ws = [torch.randn(64, 64, device=DEV) * 0.2 for _ in range(n_proj)]
+    bs = [torch.randn(64, device=DEV) * 0.1 for _ in range(n_proj)]
+    agg = F_.spmm_raw(g.fwd, X, 64, torch.empty(n, 64, device=DEV), dis, dis, True)
+    want = [torch.relu(agg.double() @ W.double() + b.double()) for W, b in zip(Ws, bs)]
+    Hs = [torch.empty(n, 64, device=DEV) for _ in range(n_proj)]
+    out = F_.spmm_proj_raw(g.fwd, X, torch.empty(n, 64, device=DEV), dis, dis, True, list(zip(Ws, bs, Hs)), relu=True)
+    assert torch.equal(out, agg)
+    for H, w in zip(Hs, want):
+        assert rel_err(H, w) < 1e-5
+    ids = torch.randperm(n, device=DEV)[:max(1, n // 6)]
+    bm = F_.mark_rows(ids, n)
+    marked = torch.zeros(n, dtype=torch.bool, device=DEV)
+    marked[ids] = True
+    Hf = [torch.full((n, 64), -5.0, device=DEV) for _ in range(n_proj)]
+    outf = torch.full((n, 64), -5.0, device=DEV)
+    F_.spmm_proj_raw(g.fwd, X, outf, dis, dis, True, list(zip(Ws, bs, Hf)), relu=True, active_rows=bm)
+    assert torch.equal(outf[marked], agg[marked]) and bool((outf[~marked] == -5.0).all())
+    for H, full in zip(Hf, Hs):
+        assert torch.equal(H[marked], full[marked]) and bool((H[~marked] == -5.0).all())

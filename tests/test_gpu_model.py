@@ -338,7 +338,7 @@ def SyntheticHIN_small():
 def test_demand_driven_loss_equals_full_propagation(kind, entity_aware, shape):
     """loss() with ``demand_driven_loss`` computes the last step only on the batch's user / item rows
     (reference models/base.py:209-210 reads nothing else): same loss, same gradients, and every
-    representation row it does compute is the full propagation's row, bit for bit."""
+    representation row it does compute is the full propagation's row."""
     ds = _dataset(shape)
     batch = _batch(ds, 512, entity_aware).to(DEV)
     model = product_model_for(ds, kind, entity_aware=entity_aware)
@@ -352,8 +352,10 @@ def test_demand_driven_loss_equals_full_propagation(kind, entity_aware, shape):
     lean = model.loss(batch)
     lean.backward()
     rows = torch.unique(batch[:, :3].reshape(-1))
-    assert torch.equal(model.cached_repr.detach()[rows], ref_repr[rows])
-    assert abs(lean.item() - full.item()) <= 1e-6 * abs(full.item())
+    # (PEAGCN: the first projection rides in the aggregation's epilogue as plain fp32 FMAs there, as a 3xTF32 tensor-core
+    # product on the full path - the same numbers to fp32 rounding, not bit for bit)
+    assert rel_err(model.cached_repr.detach()[rows], ref_repr[rows]) < 2e-6
+    assert abs(lean.item() - full.item()) <= 2e-6 * abs(full.item())
     for n, p in model.named_parameters():
         if float(ref_grads[n].abs().max()) > 1e-12:
             assert rel_err(p.grad, ref_grads[n]) < 1e-5, n
