@@ -578,7 +578,7 @@ def gcn_forward(model, metapath_idx=None, plan=None, active=None):
         l0, l1 = ch.gnn_layers
         params.extend([l0.weight, l0.bias, l1.weight, l1.bias])
     plan.head_params = [(params[4 * p].detach(), params[4 * p + 1].detach()) for p in range(plan.P)] \
-        if (lean and getattr(model, 'fuse_first_projection', True)) else None
+        if (lean and getattr(model, 'fuse_first_projection', False)) else None
     a1 = _GcnHead.apply(model.x, plan, plan.head_row_bitmaps(active) if lean else None)
     h1_full = plan.head_h1 if lean else None
     plan.head_params = None

@@ -153,6 +153,10 @@ class PEABaseRecsysModel(GraphRecsysModel):
     batch_last_step = True     # one aggregation per distinct last-step relation (columns concatenated)
     fused_engine = True        # engine.py: head / body autograd nodes instead of one node per kernel
     demand_driven_loss = False  # loss() computes only the representation rows its batch reads (BaseSolver turns it on)
+    fuse_first_projection = False   # True (PEAGCN, demand-driven steps): relu(A_hat x W1 + b1) is computed in the EPILOGUE of the
+                                    # first-step aggregation (peagnn_spmm_proj, north_star (2)) instead of by the tensor-core
+                                    # projection kernels.  Parity-tested, but measured slower at every shape (ML-25M step 6.2 ->
+                                    # 7.3 ms: 8 kFLOP of dependent fp32 FMAs per row in a latency-bound epilogue), so it is off.
     gather_dtype = 'fp32'       # 'bf16' (opt-in, PEAGCN engine): the first-step aggregations gather a bf16 copy of their
                                 # table - fp32 accumulation and outputs, results within the tolerance of tests/test_gpu_bf16.py
 

@@ -332,7 +332,7 @@ def SyntheticHIN_small():
     return SyntheticHIN('tiny', seed=7, sampling_strategy='unseen')
 
 
-@pytest.mark.parametrize('kind', ['gcn', 'sage', 'gat'])
+@pytest.mark.parametrize('kind', ['gcn', 'sage', 'gat', 'gcn+fused-first-projection'])
 @pytest.mark.parametrize('entity_aware', [False, True])
 @pytest.mark.parametrize('shape', ['tiny', 'ml-small'])
 def test_demand_driven_loss_equals_full_propagation(kind, entity_aware, shape):
@@ -341,7 +341,8 @@ def test_demand_driven_loss_equals_full_propagation(kind, entity_aware, shape):
     representation row it does compute is the full propagation's row."""
     ds = _dataset(shape)
     batch = _batch(ds, 512, entity_aware).to(DEV)
-    model = product_model_for(ds, kind, entity_aware=entity_aware)
+    model = product_model_for(ds, kind.split('+')[0], entity_aware=entity_aware)
+    model.fuse_first_projection = kind.endswith('fused-first-projection')     # peagnn_spmm_proj in the head (off by default)
     model.train()
     full = model.loss(batch)
     full.backward()
