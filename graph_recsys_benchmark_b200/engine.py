@@ -27,7 +27,11 @@ _side_streams = {}
 PARALLEL_BRANCHES = True      # False: _Fork runs its branches in order on the current stream (per-kernel timing builds)
 
 
-def fork_streams(device, n_streams=4):
+N_BRANCHES = int(__import__('os').environ.get('PEAGNN_BRANCHES', '4'))     # side streams per device
+
+
+def fork_streams(device, n_streams=None):
+    n_streams = n_streams or N_BRANCHES
     key = (device.index, n_streams)
     if key not in _side_streams:
         _side_streams[key] = [torch.cuda.Stream(device=device) for _ in range(n_streams)]
@@ -41,7 +45,7 @@ class _Fork(object):
     parallel branches they fill the GPU together.  Inside a CUDA-graph capture the branches become parallel
     paths of the graph.  Buffers that outlive the block are allocated by the caller BEFORE entering it."""
 
-    def __init__(self, device, n_streams=4):
+    def __init__(self, device, n_streams=None):
         self.streams = fork_streams(device, n_streams)
         self.device = device
 
@@ -261,26 +265,37 @@ class GcnPlan(object):
         return self._src_range
 
     def last_forward(self, t2, z, bias_all, active=None):
-        """``active``: only the marked destination rows of the last step are aggregated (the rest of z stays 0)."""
+        """``active``: only the marked destination rows of the last step are aggregated (the rest of z is not written).
+        The relation groups own disjoint column ranges: parallel branches."""
         D, start = self.repr, 0
+        jobs = []
         for g, members in self.groups:
             width = len(members) * D
-            rs, cs, loop = self._scales(g, False)
-            F_.spmm_raw(g.fwd, t2[:, start:start + width], width, z[:, start:start + width], rs, cs, loop,
-                        bias_all[start:start + width], active_rows=active.bitmap if active is not None else None)
+            g.fwd.view(width)                                    # structures / workspaces before the fork
+            jobs.append((g, start, width, self._scales(g, False)))
             start += width
+        with _Fork(t2.device) as fork:
+            for k, (g, start, width, (rs, cs, loop)) in enumerate(jobs):
+                with fork.on(k):
+                    F_.spmm_raw(g.fwd, t2[:, start:start + width], width, z[:, start:start + width], rs, cs, loop,
+                                bias_all[start:start + width], active_rows=active.bitmap if active is not None else None)
 
     def last_backward(self, dz, active=None):
-        """``active``: dz is zero outside the marked rows, so the transposed pass skips every other edge."""
+        """``active``: dz is zero outside the marked rows, so the transposed pass skips every other edge.
+        (The implicit self-loop term of row i reads dz[i], which is zero wherever i is not marked: exact.)"""
         dt2 = torch.empty_like(dz)
         D, start = self.repr, 0
+        jobs = []
         for g, members in self.groups:
             width = len(members) * D
-            rs, cs, loop = self._scales(g, True)
-            # (the implicit self-loop term of row i reads dz[i], which is zero wherever i is not marked: exact)
-            F_.spmm_raw(g.bwd, dz[:, start:start + width], width, dt2[:, start:start + width], rs, cs, loop,
-                        active_cols=active.bitmap if active is not None else None)
+            g.bwd.view(width)
+            jobs.append((g, start, width, self._scales(g, True)))
             start += width
+        with _Fork(dz.device) as fork:
+            for k, (g, start, width, (rs, cs, loop)) in enumerate(jobs):
+                with fork.on(k):
+                    F_.spmm_raw(g.bwd, dz[:, start:start + width], width, dt2[:, start:start + width], rs, cs, loop,
+                                active_cols=active.bitmap if active is not None else None)
         return dt2
 
     @staticmethod
