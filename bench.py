@@ -579,13 +579,25 @@ def product_train(c):
     strong = None
     if world > 1 and not args.no_strong and B % world == 0:
         small = make_batches(ds, B // world, K + W, seed=500 + rank).to(dev)
+        sstep = eager_step
+        if graphed is not None:                                   # the same captured form as the weak-scaling legs
+            ok = torch.ones(1, device=dev)
+            try:
+                sgraph = GraphedTrainStep(model, opt, small[0], allreduce=allreduce_grads)
+                sstep = sgraph
+            except Exception as exc:                              # noqa: BLE001
+                sys.stderr.write('strong-leg capture failed (%s: %s)\n' % (type(exc).__name__, exc))
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() < 0.5:
+                sstep = eager_step
         for k in range(W):
-            eager_step(small[k])
+            sstep(small[k])
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         s0.record()
         for k in range(K):
-            losses[2 * K].copy_(eager_step(small[W + k]))
+            losses[2 * K].copy_(sstep(small[W + k]))
         s1.record()
         barrier()
         strong = s0.elapsed_time(s1)

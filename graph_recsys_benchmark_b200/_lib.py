@@ -39,6 +39,8 @@ SIGNATURES = {
     'peagnn_launch_count': (C.c_ulonglong, []),
     'peagnn_csr_workspace_bytes': (_SZ, [_I64, _I32]),
     'peagnn_csr_build': (_INT, [_P, _P, _I64, _I32, _INT, _P, _P, _P, _P, _SZ, _P]),
+    'peagnn_csr_filter_workspace_bytes': (_SZ, [_I64]),
+    'peagnn_csr_filter': (_INT, [_G, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     'peagnn_degree_scale': (_INT, [_P, _I32, _F, _F, _INT, _P, _P]),
     'peagnn_partial_floats': (_SZ, [_I32, _I32, _I32]),
     'peagnn_spmm': (_INT, [_G, _P, _I64, _I32, _P, _I64, _P, _P, _INT, _P, _INT, _INT, _P]),

@@ -2,6 +2,7 @@
 // -> int32 CSR grouped by one endpoint, stable in COO order; degree scalings of GCN / SAGE.
 // Integer work, bit-exact against oracle/graph.py::csr_by_key.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include "common.cuh"
@@ -67,6 +68,44 @@ __global__ void degree_scale_kernel(const int32_t* __restrict__ rowptr, int32_t 
   else if (power == -1.f) r = d > 0.f ? 1.f / d : 0.f;
   else r = powf(d, power);
   out[i] = r;
+}
+
+// ---- per-step sub-structure of a CSR: only the edges whose gathered node is marked -------------------------------
+__global__ void filter_flags_kernel(const int32_t* __restrict__ col, int64_t E, const uint32_t* __restrict__ active,
+                                    int32_t* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
+    const int c = __ldg(col + e);
+    flags[e] = (int32_t)((__ldg(active + (c >> 5)) >> (c & 31)) & 1u);
+  }
+}
+
+__global__ void filter_fill_kernel(const int32_t* __restrict__ col, const int32_t* __restrict__ perm, int64_t E,
+                                   const int32_t* __restrict__ flags, const int32_t* __restrict__ pos,
+                                   int32_t* __restrict__ col_out, int32_t* __restrict__ perm_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
+    if (flags[e]) {
+      const int32_t k = pos[e];
+      col_out[k] = col[e];
+      if (perm_out) perm_out[k] = perm ? perm[e] : (int32_t)e;
+    }
+  }
+}
+
+__global__ void filter_rowptr_kernel(const int32_t* __restrict__ rowptr, int32_t nrows, int64_t E,
+                                     const int32_t* __restrict__ flags, const int32_t* __restrict__ pos,
+                                     int32_t* __restrict__ rowptr_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nrows) return;
+  const int64_t e = rowptr[i];
+  rowptr_out[i] = e < E ? pos[e] : (E > 0 ? pos[E - 1] + flags[E - 1] : 0);
+}
+
+static size_t scan_temp_bytes(int64_t E) {
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int32_t*)nullptr, (int32_t*)nullptr, (int)E);
+  return tb;
 }
 
 static size_t sort_temp_bytes(int64_t E, int bits) {
@@ -137,6 +176,50 @@ extern "C" int peagnn_csr_build(const int64_t* key, const int64_t* val, int64_t 
   const int rblocks = (int)imin64(((int64_t)N + 1 + threads - 1) / threads, (int64_t)kNumSMs * 16);
   csr_rowptr_kernel<<<rblocks, threads, 0, stream>>>(k_out, E, N, rowptr);
   return check_launch("peagnn_csr_build(rowptr)");
+}
+
+extern "C" size_t peagnn_csr_filter_workspace_bytes(int64_t E) {
+  if (E <= 0) return 256;
+  return 2 * align256((size_t)E * 4) + align256(scan_temp_bytes(E)) + 256;
+}
+
+extern "C" int peagnn_csr_filter(const peagnn_csr_t* g, const uint32_t* active_cols, const int32_t* perm,
+                                 int32_t* rowptr_out, int32_t* col_out, int32_t* perm_out, void* workspace,
+                                 size_t workspace_bytes, peagnn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PEAGNN_REQUIRE(g && g->rowptr && active_cols && rowptr_out && g->row_offset == 0, "peagnn_csr_filter: bad arguments");
+  const int64_t E = g->nnz;
+  PEAGNN_REQUIRE(E >= 0 && E < ((int64_t)1 << 31) - 1, "peagnn_csr_filter: the view must carry its edge count (nnz)");
+  if (E == 0) {
+    cudaMemsetAsync(rowptr_out, 0, sizeof(int32_t) * ((size_t)g->nrows + 1), stream);
+    return check_launch("peagnn_csr_filter(memset)");
+  }
+  PEAGNN_REQUIRE(g->col && col_out && workspace, "peagnn_csr_filter: null pointer");
+  if (workspace_bytes < peagnn_csr_filter_workspace_bytes(E)) {
+    set_error("peagnn_csr_filter: workspace %zu < %zu bytes", workspace_bytes, peagnn_csr_filter_workspace_bytes(E));
+    return PEAGNN_ERR_WORKSPACE;
+  }
+  char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  const size_t seg = align256((size_t)E * 4);
+  int32_t* flags = reinterpret_cast<int32_t*>(ws);
+  int32_t* pos = reinterpret_cast<int32_t*>(ws + seg);
+  void* temp = ws + 2 * seg;
+  size_t temp_bytes = scan_temp_bytes(E);
+  const int threads = 256;
+  const int blocks = (int)imin64((E + threads - 1) / threads, (int64_t)kNumSMs * 16);
+  filter_flags_kernel<<<blocks, threads, 0, stream>>>(g->col, E, active_cols, flags);
+  int rc = check_launch("peagnn_csr_filter(flags)");
+  if (rc) return rc;
+  cudaError_t ce = cub::DeviceScan::ExclusiveSum(temp, temp_bytes, flags, pos, (int)E, stream);
+  if (ce != cudaSuccess) {
+    set_error("peagnn_csr_filter(scan): %s", cudaGetErrorString(ce));
+    return PEAGNN_ERR_CUDA;
+  }
+  filter_fill_kernel<<<blocks, threads, 0, stream>>>(g->col, perm, E, flags, pos, col_out, perm_out);
+  rc = check_launch("peagnn_csr_filter(fill)");
+  if (rc) return rc;
+  filter_rowptr_kernel<<<(g->nrows + 1 + threads - 1) / threads, threads, 0, stream>>>(g->rowptr, g->nrows, E, flags, pos, rowptr_out);
+  return check_launch("peagnn_csr_filter(rowptr)");
 }
 
 extern "C" int peagnn_degree_scale(const int32_t* rowptr, int32_t N, float add, float power,

@@ -13,6 +13,7 @@ from . import _lib
 from .graph import _ptr, _stream, _on
 
 NEG_SLOPE = 0.2
+SHARE_FILTERED_WALK = True     # demand-driven GAT backward: per-step sub-structure of the transposed relation (Csr.filtered)
 
 
 def _req(t, name, dim=2):
@@ -402,17 +403,25 @@ class _GatAggregate(torch.autograd.Function):
         dH = torch.empty_like(H)
         vf = graph.fwd.view(feat, heads)
         vb = graph.bwd.view(feat, heads)
+        perm = graph.bwd_to_fwd
         if active is not None:
             vf = _filtered_view(vf, active_rows=active)
-            vb = _filtered_view(vb, active_cols=active)
-        perm = graph.bwd_to_fwd
+            if SHARE_FILTERED_WALK and not graph.bwd.explicit_self_loops and hasattr(graph.bwd, 'filtered'):
+                # one pass over the relation's index array per step (shared by every metapath that ends with it)
+                # instead of one column-filtered walk per metapath
+                sub = graph.bwd.filtered(active, perm)
+                vb, perm = sub.view(feat, heads), sub.perm
+            else:
+                vb = _filtered_view(vb, active_cols=active)
         with _on(dev):
+            kind = ('_filtered' if active is not None else '') + '_f%d_e%d' % (feat, nnz)
             _lib.call('peagnn_gat_backward_dst', C.byref(vf), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
                       NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), _ptr(dout), dout.stride(0),
-                      _ptr(alpha_e), _ptr(ds_e), _ptr(alpha_s), _ptr(ds_s), _ptr(d_ai), _stream())
+                      _ptr(alpha_e), _ptr(ds_e), _ptr(alpha_s), _ptr(ds_s), _ptr(d_ai), _stream(),
+                      tag='gat_backward_dst' + kind if _lib.profile is not None else None)
             _lib.call('peagnn_gat_backward_src', C.byref(vb), _ptr(perm), _ptr(alpha_e), _ptr(ds_e), _ptr(alpha_s),
                       _ptr(ds_s), _ptr(dout), dout.stride(0), feat, heads, _ptr(dH), dH.stride(0), _ptr(d_aj),
-                      _stream())
+                      _stream(), tag='gat_backward_src' + kind if _lib.profile is not None else None)
         return dH, d_ai, d_aj, db, None, None, None, None
 
 

@@ -137,10 +137,59 @@ class Csr(object):
             v.partial = part.data_ptr()
         return v
 
+    def filtered(self, bitmap, perm=None):
+        """Sub-structure holding only the edges that gather a node marked in ``bitmap`` (``functional.mark_rows``),
+        original order kept; built once per (structure, bitmap) - every metapath that ends with this relation in a
+        demand-driven step shares it - into persistent buffers (rowptr / col / perm at full capacity)."""
+        cache = getattr(bitmap, '_sub_csr', None)
+        if cache is None:
+            cache = bitmap._sub_csr = {}
+        hit = cache.get(id(self))
+        if hit is not None:
+            return hit
+        dev = self.rowptr.device
+        if getattr(self, '_filt_buf', None) is None:
+            ws_bytes = int(_lib.query('peagnn_csr_filter_workspace_bytes', self.nnz))
+            self._filt_buf = (torch.empty(self.num_nodes + 1, dtype=torch.int32, device=dev),
+                              torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev),
+                              torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev),
+                              torch.empty(ws_bytes, dtype=torch.uint8, device=dev), ws_bytes)
+        rowptr, col, perm_out, ws, ws_bytes = self._filt_buf
+        view = self.view(4)
+        with _on(dev):
+            _lib.call('peagnn_csr_filter', C.byref(view), _ptr(bitmap), _ptr(perm), _ptr(rowptr), _ptr(col), _ptr(perm_out),
+                      _ptr(ws), ws_bytes, _stream())
+        sub = cache[id(self)] = FilteredCsr(self, rowptr, col, perm_out)
+        return sub
+
     def row_shard(self, lo, hi):
         """The rows [lo, hi) as their own structure (1D destination-row sharding).
         ``col`` stays global; offsets stay absolute into the shared ``col`` array."""
         return CsrShard(self, lo, hi)
+
+
+class FilteredCsr(object):
+    """What ``Csr.filtered`` returns: the kept edges of a structure for one step.  Its edge count lives on the device
+    only, so there is no heavy-row list - a kept row is short (a source's neighbours inside one batch)."""
+
+    def __init__(self, parent, rowptr, col, perm):
+        self.parent, self.rowptr, self.col, self.perm = parent, rowptr, col, perm
+        self.num_nodes = parent.num_nodes
+        self._views = {}
+
+    def view(self, feat, heads=1):
+        v = self._views.get((feat, heads))
+        if v is None:
+            v = self._views[(feat, heads)] = _lib.CsrView()
+            v.rowptr = self.rowptr.data_ptr()
+            v.col = self.col.data_ptr()
+            v.nrows = self.num_nodes
+            v.nnz = self.num_nodes                      # scheduling hint only: sparse, several rows per warp
+            v.row_offset = 0
+            v.heavy_threshold = 2 ** 31 - 1
+            v.n_heavy = v.n_chunks = 0
+            v.explicit_self_loops = int(self.parent.explicit_self_loops)
+        return v
 
 
 class CsrShard(object):

@@ -102,6 +102,17 @@ typedef struct {
 /* Floats of `partial` workspace an aggregation of width F (per head) needs on this view. */
 size_t peagnn_partial_floats(int32_t n_chunks, int32_t feat, int32_t heads);
 
+/* Per-step sub-structure of a CSR (demand-driven steps): keeps only the edges whose gathered node (col) is marked in
+ * active_cols, in their original order.  rowptr_out[nrows + 1]; col_out / perm_out have room for nnz entries (only the
+ * first rowptr_out[nrows] are written); perm_out[k] = perm[e] of the kept edge e (perm may be NULL: e itself; perm_out
+ * may be NULL).  The view must carry nnz and row_offset = 0.  One flag pass + one CUB scan + one compaction pass over
+ * the index array; every metapath that ends with the same relation then walks the small structure instead of all edges. */
+size_t peagnn_csr_filter_workspace_bytes(int64_t num_edges);
+int peagnn_csr_filter(const peagnn_csr_t* g, const uint32_t* active_cols, const int32_t* perm, int32_t* rowptr_out,
+                      int32_t* col_out, int32_t* perm_out, void* workspace, size_t workspace_bytes,
+                      peagnn_stream_t stream);
+
+
 /* ------------------------------------------------------------------------------------------
  * K1/K2: weighted CSR aggregation (GCNConv / SAGEConv message passing, and their transposes).
  *   out[i,:] = rs[i] * ( sum_{e in row i} cs[col_e] * X[col_e,:]  +  self_loop * cs[i] * X[i,:] )
