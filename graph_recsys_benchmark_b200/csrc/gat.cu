@@ -414,7 +414,7 @@ extern "C" int peagnn_gat_backward_src(const peagnn_csr_t* gt, const int32_t* pe
     op.alpha_self = alpha_self; op.ds_self = ds_self; op.dout = dout; op.ldd = ldd;                 \
     op.feat = feat; op.f4 = feat / 4; op.dH = dH; op.ldh = ldh; op.d_aj = d_aj;                     \
     op.row_offset = gt->row_offset; op.h_ = 0; op.self_loop = !gt->explicit_self_loops;             \
-    if (gt->active_cols) return launch_csr<GatBwdSrcOp<CPL_, G_>, G_, true>(*gt, op, stream, "peagnn_gat_backward_src"); \
+    if (gt->active_cols || gt->active_rows) return launch_csr<GatBwdSrcOp<CPL_, G_>, G_, true>(*gt, op, stream, "peagnn_gat_backward_src"); \
     return launch_csr<GatBwdSrcOp<CPL_, G_>, G_>(*gt, op, stream, "peagnn_gat_backward_src");       \
   }
   PEAGNN_GEOM_DISPATCH(feat, CALL);

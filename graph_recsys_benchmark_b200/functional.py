@@ -399,8 +399,8 @@ class _GatAggregate(torch.autograd.Function):
         alpha_s = alloc(n, heads, dtype=torch.float32, device=dev)
         ds_s = alloc(n, heads, dtype=torch.float32, device=dev)
         d_ai = alloc(n, heads, dtype=torch.float32, device=dev)
-        d_aj = torch.empty_like(alpha_s)
-        dH = torch.empty_like(H)
+        d_aj = alloc(n, heads, dtype=torch.float32, device=dev)
+        dH = torch.zeros_like(H) if active is not None else torch.empty_like(H)
         vf = graph.fwd.view(feat, heads)
         vb = graph.bwd.view(feat, heads)
         perm = graph.bwd_to_fwd
@@ -410,7 +410,10 @@ class _GatAggregate(torch.autograd.Function):
                 # one pass over the relation's index array per step (shared by every metapath that ends with it)
                 # instead of one column-filtered walk per metapath
                 sub = graph.bwd.filtered(active, perm)
-                vb, perm = sub.view(feat, heads), sub.perm
+                # ... and only the rows that can receive a gradient are visited: the relation's sources (edges) and the
+                # batch rows (self loop); d H and d a_j are zero elsewhere
+                rows_bm = torch.bitwise_or(graph.bwd.nonempty_row_bitmap(), active)
+                vb, perm = _filtered_view(sub.view(feat, heads), active_rows=rows_bm), sub.perm
             else:
                 vb = _filtered_view(vb, active_cols=active)
         with _on(dev):

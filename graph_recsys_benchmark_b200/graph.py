@@ -137,6 +137,18 @@ class Csr(object):
             v.partial = part.data_ptr()
         return v
 
+    def nonempty_row_bitmap(self):
+        """Bitmap (``functional.mark_rows`` layout) of the rows that have at least one edge - the node ids that can
+        receive anything through this structure (one node type, contiguous upstream)."""
+        if getattr(self, '_row_bm', None) is None:
+            rp = self.rowptr.long()
+            words = (self.num_nodes + 31) // 32 + 1
+            on = torch.zeros(words * 32, dtype=torch.bool, device=rp.device)
+            on[:self.num_nodes] = (rp[1:] - rp[:-1]) > 0
+            w = (on.view(words, 32).to(torch.int64) << torch.arange(32, device=rp.device)).sum(dim=1)
+            self._row_bm = torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32).contiguous()
+        return self._row_bm
+
     def filtered(self, bitmap, perm=None):
         """Sub-structure holding only the edges that gather a node marked in ``bitmap`` (``functional.mark_rows``),
         original order kept; built once per (structure, bitmap) - every metapath that ends with this relation in a
