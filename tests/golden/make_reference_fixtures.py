@@ -37,6 +37,7 @@ CONFIGS = [
     ('ml-small', 1234, 'gat', False, 1024, True),       # configs[1]
     ('ml-small', 1234, 'sage', True, 1024, True),       # configs[2]
     ('ml-25m-lite', 1234, 'gcn', False, 4096, True),    # configs[3] schema at 1/10 of the edges
+    ('ml-25m-lite', 1234, 'gat', False, 4096, False),   # the same graph through the edge-softmax path (train steps only)
 ]
 N_STEPS = 3
 SAMPLE_ROWS = 512
@@ -174,14 +175,21 @@ def compact(e):
 
 
 def main():
+    """``--only KEY [KEY ...]`` regenerates just those entries and merges them into the existing file."""
     from oracle import ref_loader
     assert ref_loader.available(), 'this script runs the reference out of /root/reference'
     torch.set_num_threads(os.cpu_count() or 1)
-    fixtures = {'_meta': {'generator': 'tests/golden/make_reference_fixtures.py', 'run': RUN, 'n_steps': N_STEPS,
-                          'torch': torch.__version__, 'numpy': np.__version__,
-                          'note': 'reference code executed from /root/reference; convs = oracle/pyg150.py'}}
+    only = sys.argv[sys.argv.index('--only') + 1:] if '--only' in sys.argv else None
+    if only:
+        fixtures = torch.load(OUT, weights_only=False)
+    else:
+        fixtures = {'_meta': {'generator': 'tests/golden/make_reference_fixtures.py', 'run': RUN, 'n_steps': N_STEPS,
+                              'torch': torch.__version__, 'numpy': np.__version__,
+                              'note': 'reference code executed from /root/reference; convs = oracle/pyg150.py'}}
     for shape, gseed, kind, ea, B, evaluate in CONFIGS:
         k = key_of(shape, kind, ea)
+        if only and k not in only:
+            continue
         print(k, flush=True)
         ds = build_inputs(shape, gseed, ea)
         e = {'graph_seed': gseed}

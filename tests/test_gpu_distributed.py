@@ -195,7 +195,7 @@ def test_nccl_sharded_model_matches_unsharded(kind, world):
     if torch.cuda.device_count() < world:
         pytest.skip('needs %d GPUs, this box has %d' % (world, torch.cuda.device_count()))
     ret = mp.Manager().dict()
-    fixture = 'ml-25m-lite/gcn/plain' if kind == 'gcn' else None
+    fixture = 'ml-25m-lite/%s/plain' % kind            # judged against the reference's fp64 run of the same configuration
     mp.spawn(_worker, args=(world, _free_port(), kind, False, ret, 'ml-25m-lite', 'nccl', 4096, fixture), nprocs=world, join=True)
     _check(ret, world)
 

@@ -22,7 +22,7 @@ from graph_recsys_benchmark_b200.datasets import SyntheticHIN                   
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_runs.pt')
 CASES = ['tiny/gcn/plain', 'tiny/gat/plain', 'tiny/sage/ea', 'ml-small/gcn/plain', 'ml-small/gat/plain',
-         'ml-small/sage/ea', 'ml-25m-lite/gcn/plain']
+         'ml-small/sage/ea', 'ml-25m-lite/gcn/plain', 'ml-25m-lite/gat/plain']
 _cache = {}
 
 

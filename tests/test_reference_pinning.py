@@ -122,7 +122,7 @@ def test_product_sampling_and_init_follow_the_reference_streams():
 
 FROZEN = [('tiny', 'gcn', False, True), ('tiny', 'gat', False, True), ('tiny', 'sage', True, True),
           ('ml-small', 'gcn', False, True), ('ml-small', 'gat', False, True), ('ml-small', 'sage', True, True),
-          ('ml-25m-lite', 'gcn', False, False)]
+          ('ml-25m-lite', 'gcn', False, False), ('ml-25m-lite', 'gat', False, False)]
 
 
 @pytest.mark.parametrize('shape,kind,ea,evaluate', FROZEN)
