@@ -52,8 +52,8 @@ SIGNATURES = {
     'peagnn_gat_rowmax': (_INT, [_G, _P, _P, _I32, _F, _P, _P]),
     'peagnn_gat_aggregate': (_INT, [_G, _P, _I64, _I32, _I32, _P, _P, _F, _P, _P, _P, _I64, _P, _INT, _P]),
     'peagnn_gat_backward_dst': (_INT, [_G, _P, _I64, _I32, _I32, _P, _P, _F, _P, _P, _P, _I64, _P, _P, _I64,
-                                       _P, _P, _P, _P, _P, _P]),
-    'peagnn_gat_backward_src': (_INT, [_G, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P]),
+                                       _P, _P, _P, _P, _P]),
+    'peagnn_gat_backward_src': (_INT, [_G, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P]),
     'peagnn_linear': (_INT, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _INT, _P, _INT, _INT, _P, _I64, _P, _I64, _P]),
     'peagnn_wgrad_workspace_floats': (_SZ, [_I64, _I32, _I32]),
     'peagnn_linear_wgrad': (_INT, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _I32, _INT, _P, _P, _P, _SZ, _P]),

@@ -27,7 +27,14 @@
 //                                             warp (slots without an edge get valid = false, c = a
 //                                             safe row id, w = w2 = 0)
 //   void  finish(acc, i, h, gl, writer)       epilogue for the row; `writer` lanes (slot 0) store
+// An Op that declares `static constexpr bool kBatchDot = true` (GAT backward, destination side: a dot product of
+// the gathered row with a per-row vector, then scalar work per edge) supplies instead of apply():
+//   float partial(c, gl)                      this lane's part of <row vector, gathered row c>
+//   void  edge_done(acc, e, w, dot, valid)    one LANE per edge: the scalar work and the per-edge stores
+// and the engine reduces the 32 dot products of a batch together (process_batches_dot).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace peagnn {
@@ -51,6 +58,11 @@ template <class Op>
 __device__ __forceinline__ float identity() {
   return Op::kMax ? -INFINITY : 0.f;
 }
+
+template <class Op, class = void>
+struct is_batch_dot : std::false_type {};
+template <class Op>
+struct is_batch_dot<Op, std::void_t<decltype(Op::kBatchDot)>> : std::bool_constant<Op::kBatchDot> {};
 
 // Sum over the G lanes of a slot (xor offsets < G never leave the slot).
 template <int G>
@@ -162,11 +174,101 @@ __device__ __forceinline__ void process_batches(Op& op, const int32_t* __restric
   }
 }
 
-// Fold the 32/G slots of a warp: afterwards every lane holds the row total of its chunk.
+// Transposed reduction inside a slot: every lane holds G partial sums v[0..G) (one per batch iteration); afterwards
+// lane gl of the slot holds the slot-wide total of v[gl].  G - 1 shuffles for G totals - a plain group_sum per value
+// would take G * log2(G).
+template <int G>
+__device__ __forceinline__ float slot_transpose_sum(float* v, int gl) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    const bool up = (gl & o) != 0;
+#pragma unroll
+    for (int k = 0; k < o; ++k) {
+      const float send = up ? v[k] : v[k + o];
+      const float keep = up ? v[k + o] : v[k];
+      v[k] = keep + __shfl_xor_sync(kFull, send, o);
+    }
+  }
+  return v[0];
+}
+
+// process_batches for kBatchDot ops.  The gather loop only accumulates each lane's part of the dot product of
+// every edge of the batch (no per-edge reduction, no scalar work, no store); one transposed reduction then leaves
+// the total of edge `base + lane` in lane `lane`, which already holds that edge's scalars from the coalesced batch
+// load - so the exp / softmax-gradient arithmetic runs once per batch on 32 edges and the per-edge results are
+// stored coalesced.  acc[] holds PER-LANE sums here; fold_slots adds them up over the whole warp.
+template <class Op, int G>
+__device__ __forceinline__ void process_batches_dot(Op& op, const int32_t* __restrict__ col, int first,
+                                                    int end, int step, float* acc, int lane, int safe_row) {
+  constexpr int EPW = 32 / G;
+  const int gl = lane % G;
+  const int slot = lane / G;
+  if (first >= end) return;
+  Edge cur;
+  {
+    const int e = first + lane;
+    if (e < end) {
+      cur = op.load_edge(e, __ldg(col + e));
+    } else {
+      cur.c = safe_row; cur.w = 0.f; cur.w2 = 0.f;
+    }
+  }
+  const int back = (lane % EPW) * G + lane / EPW;   // the lane that ends up with edge `lane`'s total
+  for (int base = first; base < end; base += step) {
+    Edge nxt;
+    {
+      const int e = base + step + lane;
+      if (e < end) {
+        nxt = op.load_edge(e, __ldg(col + e));
+      } else {
+        nxt.c = safe_row; nxt.w = 0.f; nxt.w2 = 0.f;
+      }
+    }
+    const int cnt = min(32, end - base);
+    float part[G];
+    if (cnt == 32) {                                // branch-free: the G gathers of a full batch are issued together
+#pragma unroll
+      for (int s = 0; s < G; ++s) part[s] = op.partial(__shfl_sync(kFull, cur.c, s * EPW + slot), gl);
+    } else {                                        // a row's tail: groups of four gathers under one warp-uniform test
+      const int steps = (cnt + EPW - 1) / EPW;
+#pragma unroll
+      for (int s0 = 0; s0 < G; s0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) part[s0 + u] = 0.f;
+        if (s0 < steps) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)              // lanes past the row's end hold the safe row
+            part[s0 + u] = op.partial(__shfl_sync(kFull, cur.c, (s0 + u) * EPW + slot), gl);
+        }
+      }
+    }
+    float tot = slot_transpose_sum<G>(part, gl);    // lane (slot, gl) : edge gl * EPW + slot
+    tot = __shfl_sync(kFull, tot, back);
+    op.edge_done(acc, base + lane, cur.w, tot, lane < cnt);
+    cur = nxt;
+  }
+}
+
+// One row's (or one chunk's) edges through whichever walk the op and the view's filters ask for.
+template <class Op, int G, bool FILT>
+__device__ __forceinline__ void walk_row(Op& op, const peagnn_csr_t& g, int first, int end, int step,
+                                         float* acc, int lane, int safe_row) {
+  if constexpr (is_batch_dot<Op>::value) {
+    process_batches_dot<Op, G>(op, g.col, first, end, step, acc, lane, safe_row);   // (no column filter for these ops)
+  } else {
+    if (FILT && g.active_cols)
+      process_batches_filtered<Op, G>(op, g.col, g.active_cols, first, end, step, acc, lane, safe_row);
+    else
+      process_batches<Op, G>(op, g.col, first, end, step, acc, lane, safe_row);
+  }
+}
+
+// Fold the 32/G slots of a warp: afterwards every lane holds the row total of its chunk.  (kBatchDot ops keep
+// per-lane sums: the fold runs over all 32 lanes.)
 template <class Op, int G>
 __device__ __forceinline__ void fold_slots(float* acc) {
 #pragma unroll
-  for (int o = G; o < 32; o <<= 1) {
+  for (int o = is_batch_dot<Op>::value ? 1 : G; o < 32; o <<= 1) {
 #pragma unroll
     for (int v = 0; v < Op::NV; ++v) acc[v] = combine<Op>(acc[v], __shfl_xor_sync(kFull, acc[v], o));
   }
@@ -190,11 +292,7 @@ __global__ void __launch_bounds__(kCtaThreads) csr_chunk_kernel(const peagnn_csr
 #pragma unroll
   for (int v = 0; v < Op::NV; ++v) acc[v] = identity<Op>();
   op.row_begin(i, h, gl);
-  if (FILT && g.active_cols)
-    process_batches_filtered<Op, G>(op, g.col, g.active_cols, cb + warp * 32, ce, kWarpsPerCta * 32, acc, lane,
-                                    g.row_offset + i);
-  else
-    process_batches<Op, G>(op, g.col, cb + warp * 32, ce, kWarpsPerCta * 32, acc, lane, g.row_offset + i);
+  walk_row<Op, G, FILT>(op, g, cb + warp * 32, ce, kWarpsPerCta * 32, acc, lane, g.row_offset + i);
   fold_slots<Op, G>(acc);
   if (lane < G) {
 #pragma unroll
@@ -291,10 +389,7 @@ __global__ void __launch_bounds__(kCtaThreads) csr_rows_kernel(const peagnn_csr_
 #pragma unroll
     for (int v = 0; v < Op::NV; ++v) acc[v] = identity<Op>();
     op.row_begin(i, h, gl);
-    if (FILT && g.active_cols)
-      process_batches_filtered<Op, G>(op, g.col, g.active_cols, start, end, 32, acc, lane, g.row_offset + i);
-    else
-      process_batches<Op, G>(op, g.col, start, end, 32, acc, lane, g.row_offset + i);
+    walk_row<Op, G, FILT>(op, g, start, end, 32, acc, lane, g.row_offset + i);
     fold_slots<Op, G>(acc);
     op.finish(acc, i, h, gl, writer);
   }

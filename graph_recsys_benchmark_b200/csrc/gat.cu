@@ -129,11 +129,15 @@ struct GatAggOp {
 // ---- backward, destination side ---------------------------------------------------------------
 // d alpha_ij = <dout_i, H_j>;  d e_ij = alpha_ij (d alpha_ij - <dout_i, agg_i>);
 // ds_ij = d e_ij * leaky'(a_i[i] + a_j[j]);  d a_i[i] = sum_j ds_ij.
+// A kBatchDot op (csr_traverse.cuh): the gather loop only accumulates each lane's part of <dout_i, H_j>; the 32 dot
+// products of a batch are reduced together and the exp / gradient arithmetic then runs one lane per edge, with the
+// (alpha, ds) pair of 32 consecutive edges stored as one coalesced 256-byte line.
 template <int CPL, int G>
 struct GatBwdDstOp {
   static constexpr int NV = 1;
   static constexpr bool kMax = false;
   static constexpr bool kUseW2 = false;
+  static constexpr bool kBatchDot = true;
   int heads;
   const float* __restrict__ H;
   int64_t ldh;
@@ -147,8 +151,7 @@ struct GatBwdDstOp {
   const float* __restrict__ agg_bias;   // subtracted from `agg` on load when non-null
   const float* __restrict__ dout;
   int64_t ldd;
-  float* __restrict__ alpha_e;
-  float* __restrict__ ds_e;
+  float2* __restrict__ ads_e;           // [nnz, heads] (alpha, ds)
   float* __restrict__ alpha_self;
   float* __restrict__ ds_self;
   float* __restrict__ d_ai;
@@ -192,33 +195,32 @@ struct GatBwdDstOp {
     e.w2 = 0.f;
     return e;
   }
-  // executed by every lane of the warp (shuffles inside)
-  __device__ __forceinline__ float edge_terms(int64_t node, float s_raw, int gl, float& alpha) const {
-    const float* xr = H + row_off((int)node, (unsigned)ldh) + h_ * feat;
+  // this lane's part of <dout_i, H_c>.  No per-lane predicate (see SpmmOp::apply): lanes beyond the row width re-read
+  // its last chunk against g_ = 0
+  __device__ __forceinline__ float partial(int c, int gl) const {
+    const float* xr = H + row_off(c, (unsigned)ldh) + h_ * feat;
     float d = 0.f;
 #pragma unroll
     for (int ch = 0; ch < CPL; ++ch) {
-      const int idx = gl + ch * G;
-      if (idx < f4) {
-        const float4 v = ldg4(xr + 4 * idx);
-        d += g_[ch].x * v.x + g_[ch].y * v.y + g_[ch].z * v.z + g_[ch].w * v.w;
-      }
+      const float4 v = ldg4(xr + 4 * min(gl + ch * G, f4 - 1));
+      d = fmaf(g_[ch].x, v.x, d);
+      d = fmaf(g_[ch].y, v.y, d);
+      d = fmaf(g_[ch].z, v.z, d);
+      d = fmaf(g_[ch].w, v.w, d);
     }
-    d = group_sum<G>(d);
-    alpha = expf(leaky(s_raw, slope) - m_) * inv_den_;
-    const float de = alpha * (d - D_);
-    return de * (s_raw > 0.f ? 1.f : slope);
+    return d;
   }
-  __device__ __forceinline__ void apply(float* acc, int e, int c, float s_raw, float, int gl, bool valid) const {
+  __device__ __forceinline__ float edge_grad(float s_raw, float dot, float& alpha) const {
+    alpha = expf(leaky(s_raw, slope) - m_) * inv_den_;
+    return alpha * (dot - D_) * (s_raw > 0.f ? 1.f : slope);
+  }
+  // one lane per edge
+  __device__ __forceinline__ void edge_done(float* acc, int e, float s_raw, float dot, bool valid) const {
+    if (!valid) return;
     float alpha;
-    const float ds = edge_terms((int64_t)c, s_raw, gl, alpha);
-    if (valid) {
-      if (gl == 0) {
-        alpha_e[(int64_t)e * heads + h_] = alpha;
-        ds_e[(int64_t)e * heads + h_] = ds;
-      }
-      acc[0] += ds;
-    }
+    const float ds = edge_grad(s_raw, dot, alpha);
+    ads_e[(int64_t)e * heads + h_] = make_float2(alpha, ds);
+    acc[0] += ds;
   }
   __device__ __forceinline__ void finish(float* acc, int i, int h, int gl, bool writer) const {
     const int64_t node = row_offset + i;
@@ -227,8 +229,9 @@ struct GatBwdDstOp {
       if (writer && gl == 0) d_ai[gi] = acc[0];
       return;
     }
+    const float dot = group_sum<G>(partial((int)node, gl));      // every lane of the slot (shuffles inside)
     float alpha;
-    const float ds = edge_terms(node, ai_ + __ldg(a_j + gi), gl, alpha);
+    const float ds = edge_grad(ai_ + __ldg(a_j + gi), dot, alpha);
     if (writer && gl == 0) {
       alpha_self[gi] = alpha;
       ds_self[gi] = ds;
@@ -245,8 +248,7 @@ struct GatBwdSrcOp {
   static constexpr bool kUseW2 = true;
   int heads;
   const int32_t* __restrict__ perm;
-  const float* __restrict__ alpha_e;
-  const float* __restrict__ ds_e;
+  const float2* __restrict__ ads_e;     // (alpha, ds) per edge, destination order: ONE 8-byte read through the permutation
   const float* __restrict__ alpha_self;
   const float* __restrict__ ds_self;
   const float* __restrict__ dout;
@@ -262,10 +264,11 @@ struct GatBwdSrcOp {
   __device__ __forceinline__ void row_begin(int, int h, int) { h_ = h; }
   __device__ __forceinline__ Edge load_edge(int e, int c) const {
     const int64_t p = (int64_t)__ldg(perm + e) * heads + h_;
+    const float2 ad = __ldg(ads_e + p);
     Edge r;
     r.c = c;
-    r.w = __ldg(alpha_e + p);
-    r.w2 = __ldg(ds_e + p);
+    r.w = ad.x;
+    r.w2 = ad.y;
     return r;
   }
   __device__ __forceinline__ void apply(float* acc, int, int c, float w, float w2, int gl, bool valid) const {
@@ -369,22 +372,25 @@ extern "C" int peagnn_gat_backward_dst(const peagnn_csr_t* g, const float* H, in
                                        int32_t heads, const float* a_i, const float* a_j, float slope,
                                        const float* rowmax, const float* denom, const float* agg,
                                        int64_t lda, const float* agg_bias, const float* dout, int64_t ldd,
-                                       float* alpha_e, float* ds_e, float* alpha_self, float* ds_self,
+                                       float* ads_e, float* alpha_self, float* ds_self,
                                        float* d_ai, peagnn_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_gat_common(g, feat, heads, "peagnn_gat_backward_dst");
   if (rc) return rc;
   PEAGNN_REQUIRE(H && a_i && a_j && rowmax && denom && agg && dout && d_ai && (g->explicit_self_loops || (alpha_self && ds_self)),
                  "peagnn_gat_backward_dst: null pointer");
-  PEAGNN_REQUIRE(ldh % 4 == 0 && lda % 4 == 0 && ldd % 4 == 0 && aligned16(H) && aligned16(agg) && aligned16(dout),
+  PEAGNN_REQUIRE(ldh % 4 == 0 && lda % 4 == 0 && ldd % 4 == 0 && aligned16(H) && aligned16(agg) && aligned16(dout) &&
+                     (reinterpret_cast<uintptr_t>(ads_e) & 7) == 0,
                  "peagnn_gat_backward_dst: alignment");
+  PEAGNN_REQUIRE(ads_e || g->nnz == 0, "peagnn_gat_backward_dst: null per-edge buffer");
+  PEAGNN_REQUIRE(!g->active_cols, "peagnn_gat_backward_dst: a column filter is not supported on the destination side");
   if (g->nrows == 0) return PEAGNN_OK;
 #define CALL(CPL_, G_)                                                                             \
   {                                                                                                \
     GatBwdDstOp<CPL_, G_> op;                                                                      \
     op.heads = heads; op.H = H; op.ldh = ldh; op.feat = feat; op.f4 = feat / 4; op.a_i = a_i;      \
     op.a_j = a_j; op.rowmax = rowmax; op.denom = denom; op.agg = agg; op.lda = lda;                \
-    op.agg_bias = agg_bias; op.dout = dout; op.ldd = ldd; op.alpha_e = alpha_e; op.ds_e = ds_e;    \
+    op.agg_bias = agg_bias; op.dout = dout; op.ldd = ldd; op.ads_e = reinterpret_cast<float2*>(ads_e); \
     op.alpha_self = alpha_self; op.ds_self = ds_self; op.d_ai = d_ai; op.slope = slope;            \
     op.row_offset = g->row_offset; op.ai_ = op.m_ = op.inv_den_ = op.D_ = 0.f; op.h_ = 0;          \
     op.self_loop = !g->explicit_self_loops;                                                        \
@@ -397,20 +403,21 @@ extern "C" int peagnn_gat_backward_dst(const peagnn_csr_t* g, const float* H, in
   return PEAGNN_OK;
 }
 
-extern "C" int peagnn_gat_backward_src(const peagnn_csr_t* gt, const int32_t* perm, const float* alpha_e,
-                                       const float* ds_e, const float* alpha_self, const float* ds_self,
+extern "C" int peagnn_gat_backward_src(const peagnn_csr_t* gt, const int32_t* perm, const float* ads_e,
+                                       const float* alpha_self, const float* ds_self,
                                        const float* dout, int64_t ldd, int32_t feat, int32_t heads,
                                        float* dH, int64_t ldh, float* d_aj, peagnn_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_gat_common(gt, feat, heads, "peagnn_gat_backward_src");
   if (rc) return rc;
   PEAGNN_REQUIRE(dout && dH && d_aj && (gt->explicit_self_loops || (alpha_self && ds_self)), "peagnn_gat_backward_src: null pointer");
-  PEAGNN_REQUIRE(ldh % 4 == 0 && ldd % 4 == 0 && aligned16(dH) && aligned16(dout), "peagnn_gat_backward_src: alignment");
+  PEAGNN_REQUIRE(ldh % 4 == 0 && ldd % 4 == 0 && aligned16(dH) && aligned16(dout) && (reinterpret_cast<uintptr_t>(ads_e) & 7) == 0,
+                 "peagnn_gat_backward_src: alignment");
   if (gt->nrows == 0) return PEAGNN_OK;
 #define CALL(CPL_, G_)                                                                              \
   {                                                                                                 \
     GatBwdSrcOp<CPL_, G_> op;                                                                       \
-    op.heads = heads; op.perm = perm; op.alpha_e = alpha_e; op.ds_e = ds_e;                         \
+    op.heads = heads; op.perm = perm; op.ads_e = reinterpret_cast<const float2*>(ads_e);            \
     op.alpha_self = alpha_self; op.ds_self = ds_self; op.dout = dout; op.ldd = ldd;                 \
     op.feat = feat; op.f4 = feat / 4; op.dH = dH; op.ldh = ldh; op.d_aj = d_aj;                     \
     op.row_offset = gt->row_offset; op.h_ = 0; op.self_loop = !gt->explicit_self_loops;             \

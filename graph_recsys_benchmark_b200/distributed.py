@@ -258,8 +258,7 @@ class _ShardGatAggregate(torch.autograd.Function):
             db = torch.empty(heads * feat, dtype=torch.float32, device=dev)
             F_.wgrad_raw(None, dout, 0, heads * feat, 0, None, db)
         fwd, bwd = rel.fwd('rm'), rel.bwd('rm')
-        alpha_e = torch.empty(max(fwd.nnz, 1), heads, dtype=torch.float32, device=dev)
-        ds_e = torch.empty_like(alpha_e)
+        ads_e = torch.empty(max(fwd.nnz, 1), heads, 2, dtype=torch.float32, device=dev)     # (alpha, ds) per edge
         d_ai = torch.empty_like(ai)
         d_aj = torch.empty_like(aj)
         dH = torch.empty(H.shape[0], heads * feat, dtype=torch.float32, device=dev)
@@ -268,8 +267,8 @@ class _ShardGatAggregate(torch.autograd.Function):
         with F_._on(dev):
             _lib.call('peagnn_gat_backward_dst', C.byref(vf), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
                       F_.NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), _ptr(dout),
-                      dout.stride(0), _ptr(alpha_e), _ptr(ds_e), _ptr(None), _ptr(None), _ptr(d_ai), _stream())
-            _lib.call('peagnn_gat_backward_src', C.byref(vb), _ptr(perm), _ptr(alpha_e), _ptr(ds_e), _ptr(None),
+                      dout.stride(0), _ptr(ads_e), _ptr(None), _ptr(None), _ptr(d_ai), _stream())
+            _lib.call('peagnn_gat_backward_src', C.byref(vb), _ptr(perm), _ptr(ads_e), _ptr(None),
                       _ptr(None), _ptr(dout), dout.stride(0), feat, heads, _ptr(dH), dH.stride(0), _ptr(d_aj), _stream())
         return dH, d_ai, d_aj, db, None, None, None
 
@@ -609,7 +608,12 @@ class ShardedGcnPlan(object):
                 dx = torch.empty(self.sp.plan.num_nodes, d.shape[1], dtype=torch.float32, device=d.device)
                 F_.spmm_raw(rel.bwd('orig'), d, d.shape[1], dx, rel.scale_orig, rel.scale_local, False)
             else:
-                F_.spmm_raw(rel.bwd('orig'), d, d.shape[1], dx, rel.scale_orig, rel.scale_local, False, accumulate=True)
+                # an accumulating launch only visits the table rows this rank's part of the relation reaches (its edges'
+                # sources and, as explicit self-loop edges, the rows it owns): re-reading and re-writing all N rows of the
+                # partial table for a relation with a handful of sources cost more than the gather itself
+                t = rel.bwd('orig')
+                F_.spmm_raw(t, d, d.shape[1], dx, rel.scale_orig, rel.scale_local, False, accumulate=True,
+                            active_rows=t.nonempty_row_bitmap())
         return dx
 
     compact_exchange = True      # exchange only each last-step relation's source-type rows (False: the whole [N, P*repr] table)

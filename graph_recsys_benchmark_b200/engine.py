@@ -204,37 +204,49 @@ class GcnPlan(object):
                     agg(g.fwd, table, x.shape[1], out, rs, cs, loop, active_rows=bm(k))
         return outs
 
-    def head_backward(self, grads):
+    def head_backward_rows(self, row_bitmaps):
+        """Rows a transposed first-step aggregation of a demand-driven step can write anything but zero to: the sources
+        of its relation (rows with an edge in the transposed structure) and - through the self loop - the rows its
+        gradient table is non-zero on (``row_bitmaps``, the rows the forward computed).  [n_rel, words]."""
+        if getattr(self, '_bwd_sources', None) is None:
+            self._bwd_sources = torch.stack([g.bwd.nonempty_row_bitmap() for g in self.first_graphs]).contiguous()
+        return torch.bitwise_or(self._bwd_sources, row_bitmaps)
+
+    def head_backward(self, grads, row_bitmaps=None):
         """d x = sum over the first-step relations of A_hat_r^T d A1_r.  The transposed aggregations are independent;
         each branch accumulates its relations into its own buffer (fixed assignment and order: deterministic) and the
-        few partial tables are added at the end."""
-        todo = [(g, F_._rows(d)) for g, d in zip(self.first_graphs, grads) if d is not None]
+        few partial tables are added at the end.  ``row_bitmaps`` (demand-driven steps): every launch but the first of
+        a buffer visits only the rows it can contribute to (head_backward_rows) instead of re-reading and re-writing
+        the whole [N, emb] partial table for a relation with a handful of sources."""
+        todo = [(g, F_._rows(d), k) for k, (g, d) in enumerate(zip(self.first_graphs, grads)) if d is not None]
         if not todo:
             return None
+        rows = self.head_backward_rows(row_bitmaps) if row_bitmaps is not None and hasattr(todo[0][0].bwd, 'nonempty_row_bitmap') else None
+        only = (lambda k, accumulate: rows[k] if (rows is not None and accumulate) else None)
         n_br = 1 if todo[0][1].shape[0] < 50000 else min(len(todo), len(fork_streams(todo[0][1].device)))
         parts = [torch.empty_like(todo[0][1]) for _ in range(n_br)]
         # opt-in bf16 gathers: worth the conversion pass only where the gather dominates (the relations with many edges)
-        use_bf16 = [self.gather_bf16 and d.shape[1] == 64 and g.bwd.nnz >= 8 * d.shape[0] for g, d in todo]
-        tables = [F_.to_bf16(d) if b else d for (g, d), b in zip(todo, use_bf16)]
+        use_bf16 = [self.gather_bf16 and d.shape[1] == 64 and g.bwd.nnz >= 8 * d.shape[0] for g, d, _ in todo]
+        tables = [F_.to_bf16(d) if b else d for (g, d, _), b in zip(todo, use_bf16)]
         aggs = [F_.spmm_bf16_raw if b else F_.spmm_raw for b in use_bf16]
         if n_br == 1:
-            for k, (g, d) in enumerate(todo):
+            for j, (g, d, k) in enumerate(todo):
                 rs, cs, loop = self._scales(g, True)
-                aggs[k](g.bwd, tables[k], d.shape[1], parts[0], rs, cs, loop, accumulate=k > 0)
+                aggs[j](g.bwd, tables[j], d.shape[1], parts[0], rs, cs, loop, accumulate=j > 0, active_rows=only(k, j > 0))
             return parts[0]
         # the two largest relations go to different branches; the rest are dealt round-robin
-        order = sorted(range(len(todo)), key=lambda k: -todo[k][0].bwd.nnz)
-        scales = [self._scales(g, True) for g, _ in todo]         # lazily built tensors and workspaces: before the fork
-        for g, d in todo:
+        order = sorted(range(len(todo)), key=lambda j: -todo[j][0].bwd.nnz)
+        scales = [self._scales(g, True) for g, _, _ in todo]      # lazily built tensors and workspaces: before the fork
+        for g, d, _ in todo:
             g.bwd.view(d.shape[1])
         seen = [False] * n_br
         with _Fork(parts[0].device) as fork:
-            for pos, k in enumerate(order):
-                g, d = todo[k]
+            for pos, j in enumerate(order):
+                g, d, k = todo[j]
                 b = pos % n_br
-                rs, cs, loop = scales[k]
+                rs, cs, loop = scales[j]
                 with fork.on(b):
-                    aggs[k](g.bwd, tables[k], d.shape[1], parts[b], rs, cs, loop, accumulate=seen[b])
+                    aggs[j](g.bwd, tables[j], d.shape[1], parts[b], rs, cs, loop, accumulate=seen[b], active_rows=only(k, seen[b]))
                 seen[b] = True
         dx = parts[0]
         for extra in parts[1:]:
@@ -322,13 +334,15 @@ class _GcnHead(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, plan, row_bitmaps=None):
         x = F_._rows(F_._req(x, 'x'))
-        ctx.plan = plan
+        ctx.plan, ctx.row_bitmaps = plan, row_bitmaps
         if row_bitmaps is not None:
             return tuple(plan.head_forward(x, row_bitmaps))
         return tuple(plan.head_forward(x))
 
     @staticmethod
     def backward(ctx, *grads):
+        if ctx.row_bitmaps is not None:
+            return ctx.plan.head_backward(grads, ctx.row_bitmaps), None, None
         return ctx.plan.head_backward(grads), None, None
 
 

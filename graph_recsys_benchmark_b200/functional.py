@@ -133,6 +133,15 @@ def mark_rows(ids, n_bits, mod=0, rem=0):
     return bitmap
 
 
+def range_bitmap(lo, hi, n_bits, device):
+    """``mark_rows`` layout with the bits lo <= id < hi set (a node type's id range)."""
+    words = (int(n_bits) + 31) // 32 + 1
+    bit = torch.arange(words * 32, device=device)
+    on = (bit >= lo) & (bit < hi)
+    w = (on.view(words, 32).to(torch.int64) << torch.arange(32, device=device)).sum(dim=1)
+    return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32).contiguous()
+
+
 def linear_algorithmic_bytes(n, K, M, accumulate=False, gated=False):
     """X once, Y once, W once (+ Y read when accumulating, + the gate's rows)."""
     return 4 * n * (K + M) + 4 * K * M + (4 * n * M if accumulate else 0) + (4 * n * M if gated else 0)
@@ -345,23 +354,47 @@ def _filtered_view(view, active_rows=None, active_cols=None):
     return v
 
 
+class NeededRows(object):
+    """Rows of an intermediate step's output that the rest of a demand-driven loss() reads: ``static`` (a bitmap fixed
+    by the metapath: the node-id range of the next relation's sources) OR the step's batch rows -> ``bitmap``."""
+
+    def __init__(self, static, bitmap):
+        self.static, self.bitmap = static, bitmap
+
+    def covers(self, csr):
+        """True when every row of ``csr`` that has an edge is marked by the static part (decided once per structure,
+        outside any capture): a row-filtered pass then still writes every per-edge slot."""
+        cache = getattr(self.static, '_covers', None)
+        if cache is None:
+            cache = self.static._covers = {}
+        hit = cache.get(id(csr))
+        if hit is None:
+            has = csr.nonempty_row_bitmap()
+            hit = cache[id(csr)] = bool((torch.bitwise_and(has, torch.bitwise_not(self.static)) == 0).all().item())
+        return hit
+
+
 class _GatAggregate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, H, ai, aj, bias, graph, heads, relu, active=None):
-        """``active`` (a bitmap): only the marked target rows are aggregated - the demand-driven last step of
-        loss(); the other rows of the output are zero."""
+    def forward(ctx, H, ai, aj, bias, graph, heads, relu, active=None, needed=None):
+        """Demand-driven forms (bitmaps from ``mark_rows``); the rows that are not marked come out as zero:
+        ``active``  a channel's LAST step - the few rows a batch reads: the target-side passes visit those rows, the
+                    source-side pass walks a per-step sub-structure holding only the edges into them;
+        ``needed``  an EARLIER step - the rows the next step reads (its relation's source type plus the batch rows):
+                    nearly every edge survives, what is skipped is the per-row work on the other node types."""
         H = _rows(_req(H, 'h'))
         n = graph.num_nodes
         feat = H.shape[1] // heads
         dev = H.device
         ai, aj = ai.contiguous(), aj.contiguous()
-        alloc = torch.zeros if active is not None else torch.empty
+        rows = active if active is not None else (needed.bitmap if needed is not None else None)
+        alloc = torch.zeros if rows is not None else torch.empty
         rowmax = alloc(n, heads, dtype=torch.float32, device=dev)
         denom = alloc(n, heads, dtype=torch.float32, device=dev)
         out = alloc(n, heads * feat, dtype=torch.float32, device=dev)
         view = graph.fwd.view(feat, heads)
-        if active is not None:
-            view = _filtered_view(view, active_rows=active)
+        if rows is not None:
+            view = _filtered_view(view, active_rows=rows)
         # SURVEY 8(d): E*(4 col + 4 a_j[src] + F*4) + N*(F*4 own row + 8 + F*4 write) + (N+1)*4, per head
         nnz = graph.fwd.nnz
         with _on(dev):
@@ -370,14 +403,14 @@ class _GatAggregate(torch.autograd.Function):
                       NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), int(relu), _stream(),
                       tag='gat_agg_f%d_e%d_n%d' % (feat, nnz, n),
                       nbytes=heads * (nnz * (8 + 4 * feat) + n * (8 * feat + 8) + (n + 1) * 4))
-        ctx.graph, ctx.heads, ctx.relu, ctx.has_bias, ctx.active = graph, heads, relu, bias is not None, active
+        ctx.graph, ctx.heads, ctx.relu, ctx.has_bias, ctx.active, ctx.needed = graph, heads, relu, bias is not None, active, needed
         ctx.save_for_backward(H, ai, aj, rowmax, denom, out, bias)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         H, ai, aj, rowmax, denom, out, bias = ctx.saved_tensors
-        graph, heads, active = ctx.graph, ctx.heads, ctx.active
+        graph, heads, active, needed = ctx.graph, ctx.heads, ctx.active, ctx.needed
         n = graph.num_nodes
         feat = H.shape[1] // heads
         dev = H.device
@@ -391,16 +424,20 @@ class _GatAggregate(torch.autograd.Function):
             db = torch.empty(heads * feat, dtype=torch.float32, device=dev)
             wgrad_raw(None, dout, 0, heads * feat, 0, None, db)
         nnz = graph.fwd.nnz
-        alpha_e = torch.empty(max(nnz, 1), heads, dtype=torch.float32, device=dev)
-        ds_e = torch.empty_like(alpha_e)
-        # demand-driven: the target-side pass visits the active rows only (dout is zero elsewhere), the source-side
-        # pass skips every edge into an inactive target; per-node outputs of skipped rows must read as zero
-        alloc = torch.zeros if active is not None else torch.empty
+        rows = active if active is not None else (needed.bitmap if needed is not None else None)
+        # (alpha, ds) per edge and head, interleaved.  `needed`: the target-side pass skips rows, the source-side pass
+        # walks every edge - an edge into a skipped row has to read as (0, 0) (no such edge when the static part of
+        # the filter covers every row that has one: the usual case, the next relation's sources ARE this one's targets)
+        unwritten = needed is not None and active is None and not needed.covers(graph.fwd)
+        ads_e = (torch.zeros if unwritten else torch.empty)(max(nnz, 1), heads, 2, dtype=torch.float32, device=dev)
+        # demand-driven: the target-side pass visits the marked rows only (dout is zero elsewhere), the source-side
+        # pass skips every edge into another target; per-node outputs of skipped rows must read as zero
+        alloc = torch.zeros if rows is not None else torch.empty
         alpha_s = alloc(n, heads, dtype=torch.float32, device=dev)
         ds_s = alloc(n, heads, dtype=torch.float32, device=dev)
         d_ai = alloc(n, heads, dtype=torch.float32, device=dev)
         d_aj = alloc(n, heads, dtype=torch.float32, device=dev)
-        dH = torch.zeros_like(H) if active is not None else torch.empty_like(H)
+        dH = torch.zeros_like(H) if rows is not None else torch.empty_like(H)
         vf = graph.fwd.view(feat, heads)
         vb = graph.bwd.view(feat, heads)
         perm = graph.bwd_to_fwd
@@ -416,24 +453,28 @@ class _GatAggregate(torch.autograd.Function):
                 vb, perm = _filtered_view(sub.view(feat, heads), active_rows=rows_bm), sub.perm
             else:
                 vb = _filtered_view(vb, active_cols=active)
+        elif needed is not None:
+            vf = _filtered_view(vf, active_rows=needed.bitmap)
+            # rows that can receive a gradient: the relation's sources (edges) and the needed rows (self loop)
+            vb = _filtered_view(vb, active_rows=torch.bitwise_or(graph.bwd.nonempty_row_bitmap(), needed.bitmap))
         with _on(dev):
-            kind = ('_filtered' if active is not None else '') + '_f%d_e%d' % (feat, nnz)
+            kind = ('_filtered' if active is not None else '_needed' if needed is not None else '') + '_f%d_e%d' % (feat, nnz)
             _lib.call('peagnn_gat_backward_dst', C.byref(vf), _ptr(H), H.stride(0), feat, heads, _ptr(ai), _ptr(aj),
                       NEG_SLOPE, _ptr(rowmax), _ptr(denom), _ptr(out), out.stride(0), _ptr(bias), _ptr(dout), dout.stride(0),
-                      _ptr(alpha_e), _ptr(ds_e), _ptr(alpha_s), _ptr(ds_s), _ptr(d_ai), _stream(),
+                      _ptr(ads_e), _ptr(alpha_s), _ptr(ds_s), _ptr(d_ai), _stream(),
                       tag='gat_backward_dst' + kind if _lib.profile is not None else None)
-            _lib.call('peagnn_gat_backward_src', C.byref(vb), _ptr(perm), _ptr(alpha_e), _ptr(ds_e), _ptr(alpha_s),
+            _lib.call('peagnn_gat_backward_src', C.byref(vb), _ptr(perm), _ptr(ads_e), _ptr(alpha_s),
                       _ptr(ds_s), _ptr(dout), dout.stride(0), feat, heads, _ptr(dH), dH.stride(0), _ptr(d_aj),
                       _stream(), tag='gat_backward_src' + kind if _lib.profile is not None else None)
-        return dH, d_ai, d_aj, db, None, None, None, None
+        return dH, d_ai, d_aj, db, None, None, None, None, None
 
 
 def gat_scores(H, att_i, att_j, heads):
     return _GatScores.apply(H, att_i, att_j, heads)
 
 
-def gat_aggregate(H, ai, aj, graph, heads, bias=None, relu=False, active=None):
-    return _GatAggregate.apply(H, ai, aj, bias, graph, heads, relu, active)
+def gat_aggregate(H, ai, aj, graph, heads, bias=None, relu=False, active=None, needed=None):
+    return _GatAggregate.apply(H, ai, aj, bias, graph, heads, relu, active, needed)
 
 
 # ---------------------------------------------------------------------------------------------

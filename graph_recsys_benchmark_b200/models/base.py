@@ -93,6 +93,7 @@ class PEABaseChannel(torch.nn.Module):
         so the model can aggregate all channels that share that relation in one launch."""
         assert len(edge_index_list) == self.num_steps
         n = x.size(0)
+        needed = self._needed_rows(edge_index_list, n, active) if active is not None else None
         for step_idx in range(self.num_steps):
             layer = self.gnn_layers[step_idx]
             ei = edge_index_list[step_idx]
@@ -109,8 +110,42 @@ class PEABaseChannel(torch.nn.Module):
                     kw['aggregated'] = shared[key]
             if last and active is not None and getattr(layer, 'supports_active', False):
                 kw['active'] = active                       # demand-driven loss(): only the rows its batch reads
+            elif not last and needed is not None and needed[step_idx] is not None:
+                kw['needed'] = needed[step_idx]             # ... and of an earlier step, only the rows the later steps read
             x = layer(x, ei, relu=not last, graph=g, **kw)
         return x
+
+    def _needed_rows(self, edge_index_list, n, active):
+        """Per step but the last: the rows of its output a demand-driven loss() reads, or None (step computes all
+        rows).  Step s+1 gathers the sources of its relation - node ids are contiguous by type upstream
+        (datasets/movielens.py:184-227), so the [min, max] id range of its source column is that type - and its self
+        loop reads the rows it produces itself: needed(s) = source range of relation s+1 OR needed(s+1), with
+        needed(last) = the batch rows.  Any superset is exact; rows outside come out as zero and receive no gradient."""
+        layers = self.gnn_layers
+        S = self.num_steps
+        if S < 2 or not getattr(layers[-1], 'supports_active', False):
+            return None
+        out = [None] * S
+        cache = getattr(active, '_needed', None)
+        if cache is None:
+            cache = active._needed = {}
+        later = active                                      # bitmap of the rows read of step s+1's output
+        for s in range(S - 2, -1, -1):
+            if not getattr(layers[s], 'supports_needed', False):
+                break
+            g_next = get_graph(edge_index_list[s + 1], n, keep_self_loops=getattr(layers[s + 1], 'keeps_self_loops', False))
+            static = getattr(g_next, '_source_range_bitmap', None)
+            if static is None:
+                col = g_next.fwd.col
+                lo, hi = (int(col.min().item()), int(col.max().item()) + 1) if col.numel() else (0, 0)
+                static = g_next._source_range_bitmap = F_.range_bitmap(lo, hi, n, active.device)
+            key = (id(static), id(later))
+            bm = cache.get(key)
+            if bm is None:
+                bm = cache[key] = torch.bitwise_or(static, later)   # shared by the channels with the same later steps
+            out[s] = F_.NeededRows(static, bm)
+            later = bm
+        return out
 
 
 class PEABaseRecsysModel(GraphRecsysModel):

@@ -33,8 +33,9 @@ class PEAGATConv(torch.nn.Module):
         zeros(self.bias)
 
     supports_active = True     # as a channel's last step, it can aggregate only the rows loss() reads
+    supports_needed = True     # ... and as an earlier step, only the rows the following steps read (functional.NeededRows)
 
-    def forward(self, x, edge_index, relu=False, graph=None, active=None):
+    def forward(self, x, edge_index, relu=False, graph=None, active=None, needed=None):
         if self.training and self.dropout > 0:
             # every shipped configuration trains with dropout 0 (experiments/peagat_solver_bpr.py:29);
             # attention dropout would need the reference's torch RNG stream reproduced per edge.
@@ -42,7 +43,7 @@ class PEAGATConv(torch.nn.Module):
         g = graph if graph is not None else get_graph(edge_index, x.size(0))
         h = F_.linear(x, self.lin.weight, None, w_is_out_in=True)
         a_i, a_j = F_.gat_scores(h, self.att_i.view(-1), self.att_j.view(-1), self.heads)
-        return F_.gat_aggregate(h, a_i, a_j, g, self.heads, self.bias, relu=relu, active=active)
+        return F_.gat_aggregate(h, a_i, a_j, g, self.heads, self.bias, relu=relu, active=active, needed=needed)
 
     def __repr__(self):
         return '{}({}, {}, heads={})'.format(self.__class__.__name__, self.in_channels, self.out_channels, self.heads)

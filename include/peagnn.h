@@ -180,21 +180,21 @@ int peagnn_gat_aggregate(const peagnn_csr_t* g, const float* H, int64_t ldh, int
                          const float* bias, int relu, peagnn_stream_t stream);
 /* Backward, destination side.  dout is the gradient of the aggregate BEFORE bias/relu;
  * `agg` - `agg_bias` (agg_bias may be NULL) is that aggregate; where a relu clamped the output
- * dout is 0, so the forward output can be passed as `agg` with the conv bias as `agg_bias`.  Writes per-edge alpha / ds (CSR order, [nnz, heads]),
- * the self-loop terms alpha_self / ds_self [N, heads] and d a_i [N, heads], where
- * ds = d loss / d (a_i[i] + a_j[j]). */
+ * dout is 0, so the forward output can be passed as `agg` with the conv bias as `agg_bias`.  Writes the per-edge
+ * pairs ads_e[e, h] = (alpha, ds) (CSR order, [nnz, heads, 2] floats, 8-byte aligned: one coalesced line per 32 edges
+ * here, one 8-byte read per edge on the source side), the self-loop terms alpha_self / ds_self [N, heads] and
+ * d a_i [N, heads], where ds = d loss / d (a_i[i] + a_j[j]).  Row filter (g->active_rows) only. */
 int peagnn_gat_backward_dst(const peagnn_csr_t* g, const float* H, int64_t ldh, int32_t feat,
                             int32_t heads, const float* a_i, const float* a_j, float slope,
                             const float* rowmax, const float* denom, const float* agg,
                             int64_t lda, const float* agg_bias, const float* dout, int64_t ldd,
-                            float* alpha_e,
-                            float* ds_e, float* alpha_self, float* ds_self, float* d_ai,
+                            float* ads_e, float* alpha_self, float* ds_self, float* d_ai,
                             peagnn_stream_t stream);
 /* Backward, source side, over the TRANSPOSED structure gt (rows = sources, col = targets);
- * perm[k] = position in the destination-ordered edge arrays of gt's k-th edge.
+ * perm[k] = position in the destination-ordered per-edge array ads_e of gt's k-th edge.
  * dH[j, h-slice] = sum alpha * dout[i, h-slice] (+ self); d a_j[j,h] = sum ds (+ self). */
-int peagnn_gat_backward_src(const peagnn_csr_t* gt, const int32_t* perm, const float* alpha_e,
-                            const float* ds_e, const float* alpha_self, const float* ds_self,
+int peagnn_gat_backward_src(const peagnn_csr_t* gt, const int32_t* perm, const float* ads_e,
+                            const float* alpha_self, const float* ds_self,
                             const float* dout, int64_t ldd, int32_t feat, int32_t heads,
                             float* dH, int64_t ldh, float* d_aj, peagnn_stream_t stream);
 

@@ -166,6 +166,10 @@ def compact(e):
             assert torch.equal(f32[k], f64[k])
             f64.pop(k, None)
             f32[k] = f32[k].to(torch.int32)
+    # how far the reference's OWN fp32 run is from its fp64 run, per parameter gradient (max-norm relative): the floor
+    # below which no fp32 implementation of this configuration can be judged
+    f32['grad_err'] = {k: float((f32['grads'][k].double() - g.double()).abs().max() / g.double().abs().max())
+                       if float(g.abs().max()) > 1e-10 else 0.0 for k, g in f64['grads'].items()}
     for k in ('repr_rows', 'x_grad_rows', 'grads', 'eval_repr_rows'):
         f32.pop(k, None)
     for k in ('repr_rows', 'x_grad_rows', 'eval_repr_rows'):

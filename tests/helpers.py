@@ -51,6 +51,30 @@ def rel_err(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
+# Parameters whose gradient contains ONE relu decision that is a tie in fp32: with the fixture seed a first-layer
+# pre-activation is zero to within fp32 rounding (GCN: metapath 2, row 21080 - profiles/r2_shard_relu_tie.txt; GAT:
+# metapath 8, row 21851 column 26, -7.4e-10 in the reference's fp64 run against a row scale of 4e-2 -
+# tools/gat_grad_diag.py), so an fp32 sum in another order lands on the other side of the relu than the fp64
+# reference and that row's upstream gradient (9.2e-4 of the largest entry for the GAT case) enters or leaves the
+# layer's weight / bias gradient.  A property of fp32, named here instead of widening every bound.
+RELU_TIES = {
+    'ml-25m-lite/gcn/plain': ('pea_channels.2.gnn_layers.0.weight', 'pea_channels.2.gnn_layers.0.bias'),
+    'ml-25m-lite/gat/plain': ('pea_channels.8.gnn_layers.0.lin.weight', 'pea_channels.8.gnn_layers.0.bias',
+                              'pea_channels.8.gnn_layers.0.att_i', 'pea_channels.8.gnn_layers.0.att_j'),
+}
+
+
+def grad_bound(fixture_key, fx, name, base=1e-4):
+    """Bound on a parameter gradient's max-norm relative error against the reference's fp64 run: ``base`` (1e-4),
+    unless the reference's OWN fp32 run is already further away than a third of that (``f32['grad_err']``, written
+    by tests/golden/make_reference_fixtures.py: long fp32 column sums with cancellation - the GAT bias gradients on
+    the 30 k-node graph are 4e-4 off in the reference itself), or the entry holds a relu tie."""
+    if name in RELU_TIES.get(fixture_key, ()):
+        return 1.5e-3
+    own = fx['f32'].get('grad_err', {}).get(name, 0.0)
+    return max(base, 3.0 * own)
+
+
 # ---------------------------------------------------------------------------------------------
 # the run tests/golden/make_reference_fixtures.py performs with the reference's code, restated
 # with the oracle (same seeds, same order of RNG consumption, same outputs)

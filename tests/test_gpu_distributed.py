@@ -92,7 +92,9 @@ def _worker(rank, world, port, kind, entity_aware, ret, shape='tiny', backend='g
         vs_truth = None
         if truth is not None:
             named = dict(model.named_parameters())
+            from helpers import grad_bound
             vs_truth = dict(
+                bounds={n: grad_bound(fixture, fx, n) for n in truth['grads']},
                 loss_sharded=abs(total.item() - truth['losses'][0]) / abs(truth['losses'][0]),
                 loss_unsharded=abs(loss_ref.item() - truth['losses'][0]) / abs(truth['losses'][0]),
                 sharded={n: rel(named[n].grad, g.cuda()) for n, g in truth['grads'].items() if float(g.abs().max()) > 1e-10},
@@ -137,21 +139,20 @@ def test_sharded_model_matches_unsharded(kind, entity_aware, world):
     _check(ret, world)
 
 
-RELU_TIE = ('pea_channels.2.gnn_layers.0.weight', 'pea_channels.2.gnn_layers.0.bias')
-
-
 def _check(ret, world):
     for r in range(world):
         out = ret[r]
         big = out.get('big', False)
-        # sharded vs unsharded, both fp32: each is within 1e-4 of the truth, so on the 30 k-node graph (column sums with
-        # cancellation) they may differ by more than that from each other; 1e-4 on the small graphs
-        pair_bound = (lambda name: 1e-3 if name in RELU_TIE else 2.5e-4) if big else (lambda name: 1e-4)
+        vt = out.get('vs_truth')
+        # sharded vs unsharded, both fp32: each is within its bound of the truth (helpers.grad_bound: 1e-4, more only
+        # where the reference's own fp32 run is further off or a relu tie sits), so they may differ from each other by
+        # twice that; 1e-4 on the small graphs
+        bounds = vt['bounds'] if vt is not None else {}
+        pair_bound = (lambda name: 2.5 * bounds.get(name, 1e-4)) if big else (lambda name: 1e-4)
         assert out['finite'], out
         assert out['loss'] < 1e-5, out
         assert out['eval_gap'] < 1e-12, out
         assert out['repr'] < 1e-5, out
-        vt = out.get('vs_truth')
         if vt is not None:
             # judged against the reference's fp64 run: the sharded model has to meet the same bound as the unsharded one
             worst_s = max(vt['sharded'].items(), key=lambda kv: kv[1])
@@ -163,11 +164,11 @@ def _check(ret, world):
                     print('   sharded %-44s %.2e   (unsharded %.2e)' % (name, e, vt['unsharded'][name]))
             assert vt['loss_sharded'] < 1e-5, vt
             for name, e in vt['sharded'].items():
-                # RELU_TIE: with this seed ONE pre-activation of metapath 2's first layer (row 21080) is zero to within fp32
-                # rounding; the shard's summation order (self loop as the row's last edge) lands on the other side of the
-                # relu than the unsharded kernel and the fp64 reference, which moves that layer's gradient by 2.5e-4 and
-                # nothing else (profiles/r2_shard_relu_tie.txt, tools/shard_diag2.py) - a property of fp32, not of sharding
-                assert e < (1e-3 if name in RELU_TIE else 1e-4), (name, e, worst_u)
+                # helpers.RELU_TIES: with this seed ONE first-layer pre-activation is zero to within fp32 rounding; the
+                # shard's summation order (self loop as the row's last edge) may land on the other side of the relu than
+                # the fp64 reference, which moves that layer's gradient and nothing else (profiles/r2_shard_relu_tie.txt,
+                # tools/shard_diag2.py, tools/gat_grad_diag.py) - a property of fp32, not of sharding
+                assert e < vt['bounds'][name], (name, e, worst_u)
         else:
             for name, e in out['grads'].items():
                 assert e < pair_bound(name), (name, e)

@@ -468,3 +468,51 @@ def test_aggregation_with_the_first_projection_in_its_epilogue(gname, n_proj):
     assert torch.equal(outf[marked], agg[marked]) and bool((outf[~marked] == -5.0).all())
     for H, full in zip(Hf, Hs):
         assert torch.equal(H[marked], full[marked]) and bool((H[~marked] == -5.0).all())
+
+
+@pytest.mark.parametrize('gname', ['small', 'heavy', 'bipartite'])
+@pytest.mark.parametrize('covering', [False, True])
+@pytest.mark.parametrize('fout', [64, 16])
+def test_gat_step_on_the_rows_the_next_step_reads(gname, covering, fout):
+    """An earlier GAT step of a demand-driven loss() (functional.NeededRows): the marked rows equal the full pass, the
+    others are zero, and with an upstream gradient that is zero outside the marked rows every gradient equals
+    the full pass's.  ``covering``: the static part of the filter holds every row that has an edge (the usual case -
+    no per-edge slot stays unwritten) / it does not (edges into skipped rows must read as zero on the source side)."""
+    from graph_recsys_benchmark_b200 import functional as F_, graph as pgraph
+    spec = dict(GRAPHS[gname])
+    n = spec.pop('n')
+    ei = random_edge_index(n, spec.pop('e'), 11, self_loops=spec.pop('loops'), multi=spec.pop('multi'), **spec)
+    old = pgraph.HEAVY_THRESHOLD, pgraph.CHUNK_EDGES
+    if gname == 'heavy':
+        pgraph.HEAVY_THRESHOLD, pgraph.CHUNK_EDGES = 64, 96
+    try:
+        pgraph.clear_cache()
+        _, p = _conv_pair('gat', 64, fout)
+        lo, hi = (0, n) if covering else (n // 2, n)
+        if covering and gname == 'bipartite':
+            lo, hi = 100, 400                                # the target type's id range
+        static = F_.range_bitmap(lo, hi, n, torch.device(DEV))
+        extra = torch.randperm(n, generator=torch.Generator().manual_seed(3))[:7].to(DEV)
+        bitmap = torch.bitwise_or(static, F_.mark_rows(extra, n))
+        needed = F_.NeededRows(static, bitmap)
+        mask = torch.zeros(n, dtype=torch.bool, device=DEV)
+        mask[lo:hi] = True
+        mask[extra] = True
+        x = torch.randn(n, 64, device=DEV)
+        w = torch.randn(n, fout, device=DEV) * mask[:, None]
+        xa = x.clone().requires_grad_(True)
+        ya = p(xa, ei.to(DEV), relu=True)
+        (ya * w).sum().backward()
+        ga = [xa.grad.clone()] + [q.grad.clone() for q in p.parameters()]
+        p.zero_grad()
+        xb = x.clone().requires_grad_(True)
+        yb = p(xb, ei.to(DEV), relu=True, needed=needed)
+        (yb * w).sum().backward()
+        gb = [xb.grad.clone()] + [q.grad.clone() for q in p.parameters()]
+        assert needed.covers(pgraph.get_graph(ei.to(DEV), n).fwd) == covering
+        assert rel_err(yb[mask], ya[mask]) < 1e-6 and float(yb[~mask].abs().max() if (~mask).any() else 0.) == 0.
+        for a, b in zip(ga, gb):
+            assert torch.isfinite(b).all() and rel_err(b, a) < 1e-6
+    finally:
+        pgraph.HEAVY_THRESHOLD, pgraph.CHUNK_EDGES = old
+        pgraph.clear_cache()
