@@ -23,7 +23,7 @@ class CsrView(C.Structure):
         ('chunk_row', C.c_void_p), ('chunk_begin', C.c_void_p), ('chunk_end', C.c_void_p),
         ('partial', C.c_void_p),
         ('nnz', C.c_int64),
-        ('explicit_self_loops', C.c_int32), ('reserved', C.c_int32),
+        ('explicit_self_loops', C.c_int32), ('sparse_filter', C.c_int32),
         ('active_rows', C.c_void_p), ('active_cols', C.c_void_p),
     ]
 

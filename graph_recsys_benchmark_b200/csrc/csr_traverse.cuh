@@ -410,10 +410,19 @@ int launch_csr(const peagnn_csr_t& g, const Op& op, cudaStream_t stream, const c
   // sparse views (most rows have no edge) pack several rows per warp so that the edge-less rows'
   // epilogues overlap; dense views keep one row per warp for parallelism and balance
   const bool sparse = g.nnz > 0 && g.nnz < 8ll * g.nrows;
-  const long long rows_per_block = (long long)kWarpsPerCta * (sparse ? kSparseRowsPerWarp : 1);
+  // a row filter that marks a few percent of the rows (a training batch): one warp per 32-row bitmap word
+  const bool few_rows = FILT && g.active_rows && g.sparse_filter;
+  const int rpw = few_rows ? 32 : sparse ? kSparseRowsPerWarp : 1;
+  const long long rows_per_block = (long long)kWarpsPerCta * rpw;
   const long long light_blocks = ((long long)g.nrows * heads + rows_per_block - 1) / rows_per_block;
   const long long blocks = heavy_blocks + light_blocks;
   if (blocks == 0) return PEAGNN_OK;
+  if constexpr (FILT) {
+    if (few_rows) {
+      csr_rows_kernel<Op, G, 32, FILT><<<(unsigned)blocks, kCtaThreads, 0, stream>>>(g, op);
+      return check_launch(what);
+    }
+  }
   if (sparse)
     csr_rows_kernel<Op, G, kSparseRowsPerWarp, FILT><<<(unsigned)blocks, kCtaThreads, 0, stream>>>(g, op);
   else

@@ -71,15 +71,7 @@ class _Fork(object):
         return False
 
 
-class ActiveSet(object):
-    """The rows of the final representation a loss() call reads (its batch's users and items).
-    ``bitmap``  one bit per node (per LOCAL row on a shard) for the filtered aggregations;
-    ``ids``     the same node ids sorted, duplicates kept ([3B], fixed size: graph-capturable), and
-    ``first``   True at the first occurrence of each id - row lists for the projections (single-GPU plans)."""
-
-    def __init__(self, bitmap, ids=None, first=None):
-        self.bitmap, self.ids, self.first = bitmap, ids, first
-        self.h1_full = None      # per metapath [N, hidden]: first-layer activations written by the head's fused epilogue
+ActiveSet = F_.ActiveRows      # bitmap + sorted id list + first-occurrence mask of the rows a loss() call reads
 
 
 class GcnPlan(object):
@@ -255,11 +247,7 @@ class GcnPlan(object):
 
     def active_bitmap(self, ids):
         """Rows of the final representation a loss on the node ids ``ids`` reads (models/base.py:209-210)."""
-        flat = ids.reshape(-1).contiguous()
-        srt = torch.sort(flat).values
-        first = torch.ones_like(srt, dtype=torch.bool)
-        first[1:] = srt[1:] != srt[:-1]
-        return ActiveSet(F_.mark_rows(flat, self.num_nodes), srt, first)
+        return F_.active_rows(ids, self.num_nodes)
 
     def source_ranges(self):
         """Per metapath: [lo, hi) node-id range holding every SOURCE of its last-step relation (node ids are

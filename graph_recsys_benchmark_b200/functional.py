@@ -53,6 +53,9 @@ def spmm_raw(csr, X, feat, out, rs=None, cs=None, self_loop=False, bias=None, re
     """One aggregation launch.  ``active_rows`` / ``active_cols`` (bitmaps from ``mark_rows``) switch to the
     demand-driven entry point: only the marked rows are written / only edges gathering a marked node are read."""
     view = csr.view(feat)
+    if active_rows is not None and few_rows_marked(active_rows, view.nrows):
+        view = _lib.CsrView.from_buffer_copy(view)
+        view.sparse_filter = 1
     tag, nbytes = None, 0
     filtered = active_rows is not None or active_cols is not None
     if _lib.profile is not None:
@@ -130,7 +133,102 @@ def mark_rows(ids, n_bits, mod=0, rem=0):
     bitmap = torch.zeros((int(n_bits) + 31) // 32 + 1, dtype=torch.int32, device=ids.device)
     with _on(ids.device):
         _lib.call('peagnn_mark_rows', _ptr(ids), ids.numel(), int(mod), int(rem), _ptr(bitmap), _stream())
+    bitmap.marked_at_most = int(ids.numel())      # host-side bound: lets a launch over the marked rows pick its schedule
     return bitmap
+
+
+def few_rows_marked(bitmap, n_rows):
+    """True when ``bitmap`` (from ``mark_rows``) is known to mark only a few percent of ``n_rows`` rows - a training
+    batch on a large graph: row-filtered launches then put one warp on each 32-row bitmap word (``sparse_filter``)."""
+    m = getattr(bitmap, 'marked_at_most', None)
+    return m is not None and 8 * m <= n_rows
+
+
+class ActiveRows(object):
+    """The rows of the final representation a loss() call reads (its batch's users and items, models/base.py:209-210):
+    ``bitmap``  one bit per node (per LOCAL row on a shard) for the row / column filters of the aggregations;
+    ``ids``     the same node ids sorted, duplicates kept ([3B]: a fixed size, so a step stays graph-capturable);
+    ``first``   True at the first occurrence of each id - row lists that must count every node once."""
+
+    def __init__(self, bitmap, ids=None, first=None):
+        self.bitmap, self.ids, self.first = bitmap, ids, first
+        self.h1_full = None      # (PEAGCN engine) first-layer activations written by the head's fused epilogue
+        self.device = bitmap.device
+
+
+def active_rows(ids, n_nodes):
+    """ActiveRows for the node ids ``ids`` (any shape, int64, CUDA): one mark pass + one sort, no host sync."""
+    flat = ids.reshape(-1).contiguous()
+    srt = torch.sort(flat).values
+    first = torch.ones_like(srt, dtype=torch.bool)
+    first[1:] = srt[1:] != srt[:-1]
+    return ActiveRows(mark_rows(flat, n_nodes), srt, first)
+
+
+class _GatherActive(torch.autograd.Function):
+    """rows ``active.ids`` of a table whose gradient is wanted once per node: forward = index_select, backward = the
+    list gradient added back into a zero table (later occurrences of a node carry exact zeros upstream)."""
+
+    @staticmethod
+    def forward(ctx, table, active):
+        ctx.active, ctx.n = active, table.shape[0]
+        return table.index_select(0, active.ids)
+
+    @staticmethod
+    def backward(ctx, d):
+        out = torch.zeros((ctx.n,) + tuple(d.shape[1:]), dtype=d.dtype, device=d.device)
+        out.index_add_(0, ctx.active.ids, d)
+        return out, None
+
+
+class _ScatterActive(torch.autograd.Function):
+    """[3B, D] rows back into a zero [N, D] table (duplicates rewrite the same row); the gradient of every node is taken
+    once, at its first occurrence on the list."""
+
+    @staticmethod
+    def forward(ctx, rows, active, n):
+        ctx.active = active
+        out = torch.zeros((n,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+        out.index_copy_(0, active.ids, rows)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a = ctx.active
+        return dout.index_select(0, a.ids) * a.first[:, None].to(dout.dtype), None, None
+
+
+def gather_active(table, active):
+    return _GatherActive.apply(table, active)
+
+
+def scatter_active(rows, active, n):
+    return _ScatterActive.apply(rows, active, n)
+
+
+def column_sum_where_nonzero(dout, active=None, needed=None):
+    """Column sums of a gradient table that is known to be zero outside a few rows: the batch rows (``active``, a
+    last step) or a node-id range plus the batch rows (``needed``, an earlier step) - the conv's bias gradient without
+    streaming all N rows.  Falls back to the whole table when neither is given."""
+    M = dout.shape[1]
+    out = torch.empty(M, dtype=torch.float32, device=dout.device)
+    if active is not None and active.ids is not None:
+        rows = dout.index_select(0, active.ids) * active.first[:, None].to(dout.dtype)
+        wgrad_raw(None, rows, 0, M, 0, None, out)
+        return out
+    if needed is not None and needed.range is not None and needed.active is not None and needed.active.ids is not None:
+        lo, hi = needed.range
+        a = needed.active
+        keep = a.first & ((a.ids < lo) | (a.ids >= hi))
+        rows = dout.index_select(0, a.ids) * keep[:, None].to(dout.dtype)
+        wgrad_raw(None, rows, 0, M, 0, None, out)
+        if hi > lo:
+            part = torch.empty_like(out)
+            wgrad_raw(None, dout[lo:hi], 0, M, 0, None, part)
+            out.add_(part)
+        return out
+    wgrad_raw(None, dout, 0, M, 0, None, out)
+    return out
 
 
 def range_bitmap(lo, hi, n_bits, device):
@@ -351,6 +449,7 @@ def _filtered_view(view, active_rows=None, active_cols=None):
     v = _lib.CsrView.from_buffer_copy(view)
     v.active_rows = active_rows.data_ptr() if active_rows is not None else None
     v.active_cols = active_cols.data_ptr() if active_cols is not None else None
+    v.sparse_filter = int(active_rows is not None and few_rows_marked(active_rows, v.nrows))
     return v
 
 
@@ -358,8 +457,9 @@ class NeededRows(object):
     """Rows of an intermediate step's output that the rest of a demand-driven loss() reads: ``static`` (a bitmap fixed
     by the metapath: the node-id range of the next relation's sources) OR the step's batch rows -> ``bitmap``."""
 
-    def __init__(self, static, bitmap):
+    def __init__(self, static, bitmap, range=None, active=None):
         self.static, self.bitmap = static, bitmap
+        self.range, self.active = range, active      # (lo, hi) of the static part when it is one id range; the batch rows
 
     def covers(self, csr):
         """True when every row of ``csr`` that has an edge is marked by the static part (decided once per structure,
@@ -387,7 +487,8 @@ class _GatAggregate(torch.autograd.Function):
         feat = H.shape[1] // heads
         dev = H.device
         ai, aj = ai.contiguous(), aj.contiguous()
-        rows = active if active is not None else (needed.bitmap if needed is not None else None)
+        active_bm = active.bitmap if isinstance(active, ActiveRows) else active
+        rows = active_bm if active is not None else (needed.bitmap if needed is not None else None)
         alloc = torch.zeros if rows is not None else torch.empty
         rowmax = alloc(n, heads, dtype=torch.float32, device=dev)
         denom = alloc(n, heads, dtype=torch.float32, device=dev)
@@ -410,7 +511,8 @@ class _GatAggregate(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         H, ai, aj, rowmax, denom, out, bias = ctx.saved_tensors
-        graph, heads, active, needed = ctx.graph, ctx.heads, ctx.active, ctx.needed
+        graph, heads, active_obj, needed = ctx.graph, ctx.heads, ctx.active, ctx.needed
+        active = active_obj.bitmap if isinstance(active_obj, ActiveRows) else active_obj
         n = graph.num_nodes
         feat = H.shape[1] // heads
         dev = H.device
@@ -421,8 +523,9 @@ class _GatAggregate(torch.autograd.Function):
         # relu clamped the output dout is already 0, so passing the forward output is exact.
         db = None
         if ctx.has_bias and ctx.needs_input_grad[3]:
-            db = torch.empty(heads * feat, dtype=torch.float32, device=dev)
-            wgrad_raw(None, dout, 0, heads * feat, 0, None, db)
+            # dout is zero outside the rows this step computed: sum only where it can be anything else
+            db = column_sum_where_nonzero(dout, active_obj if isinstance(active_obj, ActiveRows) else None,
+                                          needed if active_obj is None else None)
         nnz = graph.fwd.nnz
         rows = active if active is not None else (needed.bitmap if needed is not None else None)
         # (alpha, ds) per edge and head, interleaved.  `needed`: the target-side pass skips rows, the source-side pass

@@ -43,9 +43,9 @@ class GraphRecsysModel(torch.nn.Module):
                 ids = pos_neg_pair_t[:, :3]
                 self.cached_repr = self.forward(_active=self._plan().active_bitmap(ids))
             elif self.demand_driven_loss and sharded is None and all(ch.supports_active() for ch in self.pea_channels):
-                # per-layer path (PEAGAT): the channels' last conv takes the bitmap
-                bitmap = F_.mark_rows(pos_neg_pair_t[:, :3].reshape(-1), self.x.shape[0])
-                self.cached_repr = self.forward(_active=bitmap)
+                # per-layer path (PEAGAT): the channels' last conv aggregates the batch rows, the earlier ones the rows
+                # that feeds on, and the fusion runs on the batch rows
+                self.cached_repr = self.forward(_active=F_.active_rows(pos_neg_pair_t[:, :3], self.x.shape[0]))
             else:
                 self.cached_repr = self.forward()
         cf_loss = F_.bpr_loss(self.cached_repr, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
@@ -129,21 +129,23 @@ class PEABaseChannel(torch.nn.Module):
         cache = getattr(active, '_needed', None)
         if cache is None:
             cache = active._needed = {}
-        later = active                                      # bitmap of the rows read of step s+1's output
+        later = active.bitmap                               # bitmap of the rows read of step s+1's output
         for s in range(S - 2, -1, -1):
             if not getattr(layers[s], 'supports_needed', False):
                 break
             g_next = get_graph(edge_index_list[s + 1], n, keep_self_loops=getattr(layers[s + 1], 'keeps_self_loops', False))
-            static = getattr(g_next, '_source_range_bitmap', None)
-            if static is None:
+            hit = getattr(g_next, '_source_range_bitmap', None)
+            if hit is None:
                 col = g_next.fwd.col
                 lo, hi = (int(col.min().item()), int(col.max().item()) + 1) if col.numel() else (0, 0)
-                static = g_next._source_range_bitmap = F_.range_bitmap(lo, hi, n, active.device)
+                hit = g_next._source_range_bitmap = ((lo, hi), F_.range_bitmap(lo, hi, n, active.device))
+            rng, static = hit
             key = (id(static), id(later))
             bm = cache.get(key)
             if bm is None:
                 bm = cache[key] = torch.bitwise_or(static, later)   # shared by the channels with the same later steps
-            out[s] = F_.NeededRows(static, bm)
+            # (range, batch rows) describe the marked rows exactly only right below the last step
+            out[s] = F_.NeededRows(static, bm, rng if s == S - 2 else None, active if s == S - 2 else None)
             later = bm
         return out
 
@@ -248,8 +250,14 @@ class PEABaseRecsysModel(GraphRecsysModel):
             if ok == 'gcn':
                 return engine.gcn_forward(self, metapath_idx, plan=self._plan(), active=_active)
             return engine.sage_forward(self, metapath_idx, active=_active)
-        z = torch.stack(self.channel_outputs(_active), dim=1)           # [N, P, repr]
+        outs = self.channel_outputs(_active)
         att = self.att if self.channel_aggr == 'att' else None
+        if _active is not None and getattr(_active, 'ids', None) is not None and metapath_idx is None:
+            # demand-driven loss(): only the batch rows of the channel outputs are non-zero - fuse those [3B, P, repr]
+            # rows and put the result back into an otherwise zero table instead of stacking and fusing all N rows
+            z = torch.stack([F_.gather_active(o, _active) for o in outs], dim=1)
+            return F_.scatter_active(F_.fuse_channels(z, att, self.channel_aggr, None), _active, self.x.shape[0])
+        z = torch.stack(outs, dim=1)                                      # [N, P, repr]
         return F_.fuse_channels(z, att, self.channel_aggr, metapath_idx)
 
     def predict(self, unids, inids):

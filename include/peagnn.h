@@ -87,7 +87,9 @@ typedef struct {
                                      several rows per warp); 0 = unknown                      */
   int32_t explicit_self_loops;    /* != 0: self loops are stored as ordinary edges of the view
                                      (row shards); kernels then add no implicit self loop      */
-  int32_t reserved;
+  int32_t sparse_filter;          /* hint for active_rows: != 0 when only a few percent of the rows are marked (a
+                                     training batch) - a warp then scans one 32-row bitmap word instead of one row,
+                                     so the launch is ~nrows/256 CTAs that mostly have work, not nrows/8 that exit */
   /* optional per-call filters (NULL = none), bitmaps with bit (id & 31) of word (id >> 5):
      active_rows - only LOCAL rows whose bit is set are computed and written, the rest are left untouched;
      active_cols - edges whose gathered node id (col) has a clear bit are skipped (their table rows are

@@ -363,7 +363,10 @@ def test_wgrad_direct(K, M, n, masked, out_in):
 # ---- demand-driven aggregation (peagnn_spmm_filtered) and the deterministic gradient scatter -----------------
 @pytest.mark.parametrize('gname', ['small', 'heavy', 'bipartite'])
 @pytest.mark.parametrize('feat', [16, 64, 112])
-def test_filtered_aggregation_equals_the_full_one_on_what_it_computes(gname, feat):
+@pytest.mark.parametrize('few', [False, True])
+def test_filtered_aggregation_equals_the_full_one_on_what_it_computes(gname, feat, few):
+    """``few``: the schedule for a filter that marks a few percent of the rows (one warp per 32-row bitmap word,
+    peagnn_csr_t.sparse_filter) / the one-row-per-warp schedule - same results."""
     from graph_recsys_benchmark_b200 import functional as F_
     spec = dict(GRAPHS[gname])
     n = spec.pop('n')
@@ -375,6 +378,8 @@ def test_filtered_aggregation_equals_the_full_one_on_what_it_computes(gname, fea
     full = F_.spmm_raw(g.fwd, X, feat, torch.empty(n, feat, device=DEV), dis, dis, True)
     ids = torch.randperm(n, device=DEV)[:max(1, n // 7)]
     bitmap = F_.mark_rows(ids, n)
+    bitmap.marked_at_most = 0 if few else n                # the host-side hint only picks the schedule
+    assert F_.few_rows_marked(bitmap, n) == few
     marked = torch.zeros(n, dtype=torch.bool, device=DEV)
     marked[ids] = True
     # rows: the marked rows equal the full launch bit for bit, the others are left untouched
