@@ -28,6 +28,20 @@ class CsrView(C.Structure):
     ]
 
 
+class LinearProblem(C.Structure):
+    """Mirror of ``peagnn_linear_problem_t``."""
+    _fields_ = [('X', C.c_void_p), ('ldx', C.c_int64), ('n', C.c_int64), ('W', C.c_void_p), ('bias', C.c_void_p),
+                ('Y', C.c_void_p), ('ldy', C.c_int64), ('out_mask', C.c_void_p), ('ldom', C.c_int64)]
+
+
+class WgradProblem(C.Structure):
+    """Mirror of ``peagnn_wgrad_problem_t``."""
+    _fields_ = [('X', C.c_void_p), ('ldx', C.c_int64), ('dY', C.c_void_p), ('ldd', C.c_int64), ('n', C.c_int64),
+                ('dW', C.c_void_p), ('db', C.c_void_p)]
+
+
+MAX_GROUP = 32      # PEAGNN_MAX_GROUP
+
 _P, _I32, _I64, _INT, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_int, C.c_float, C.c_size_t
 _U64 = C.c_uint64
 _G = C.POINTER(CsrView)
@@ -55,6 +69,9 @@ SIGNATURES = {
                                        _P, _P, _P, _P, _P]),
     'peagnn_gat_backward_src': (_INT, [_G, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P]),
     'peagnn_linear': (_INT, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _INT, _P, _INT, _INT, _P, _I64, _P, _I64, _P]),
+    'peagnn_linear_grouped': (_INT, [_P, _I32, _I32, _I32, _INT, _INT, _INT, _P]),
+    'peagnn_wgrad_grouped_workspace_floats': (_SZ, [_I32, _I32, _I32]),
+    'peagnn_linear_wgrad_grouped': (_INT, [_P, _I32, _I32, _I32, _INT, _P, _SZ, _P]),
     'peagnn_wgrad_workspace_floats': (_SZ, [_I64, _I32, _I32]),
     'peagnn_linear_wgrad': (_INT, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _I32, _INT, _P, _P, _P, _SZ, _P]),
     'peagnn_relu_backward': (_INT, [_P, _I64, _P, _I64, _I64, _I32, _P, _I64, _P]),

@@ -61,4 +61,30 @@ __device__ __forceinline__ float neg_log_sigmoid(float z) {
 // d/dz of the above = sigmoid(z) - 1 = -1 / (1 + e^z); expf(z) -> inf gives -0, -> 0 gives -1
 __device__ __forceinline__ float neg_log_sigmoid_grad(float z) { return -1.f / (1.f + expf(z)); }
 
+// Grouped projection launches (peagnn_linear_grouped): the problem table travels by value in the kernel parameters
+// (it is captured with the launch by a CUDA graph); CTA b works on the problem whose block range holds b.
+struct LinearGroup {
+  int count;
+  int block_start[PEAGNN_MAX_GROUP + 1];
+  peagnn_linear_problem_t p[PEAGNN_MAX_GROUP];
+};
+__device__ __forceinline__ int group_of_block(const LinearGroup& g, int b) {
+  int k = 0;
+  while (k + 1 < g.count && b >= g.block_start[k + 1]) ++k;
+  return k;
+}
+
+struct WgradGroup {
+  int count;
+  int block_start[PEAGNN_MAX_GROUP + 1];
+  int64_t rows_per_cta[PEAGNN_MAX_GROUP];
+  float* partial[PEAGNN_MAX_GROUP];      // this problem's [parts][K*M + M] slice of the workspace
+  peagnn_wgrad_problem_t p[PEAGNN_MAX_GROUP];
+};
+__device__ __forceinline__ int group_of_block(const WgradGroup& g, int b) {
+  int k = 0;
+  while (k + 1 < g.count && b >= g.block_start[k + 1]) ++k;
+  return k;
+}
+
 }  // namespace peagnn

@@ -530,6 +530,114 @@ extern "C" int peagnn_linear(const float* X, int64_t ldx, const float* mask, int
 #undef PEAGNN_LIN_CASE
 }
 
+// ---- grouped projections ---------------------------------------------------------------------------------
+// CTAs are dealt to the problems in proportion to their 128-row tiles (at least one each); `budget` = the CTAs that are
+// resident at once for this kernel, so that a group of small problems is one wave whose CTAs each take a few tiles.
+static int fill_group(const peagnn_linear_problem_t* probs, int count, int budget, LinearGroup& g) {
+  long long total = 0;
+  for (int k = 0; k < count; ++k) total += (probs[k].n + 127) / 128;
+  g.count = count;
+  int at = 0;
+  for (int k = 0; k < count; ++k) {
+    g.p[k] = probs[k];
+    g.block_start[k] = at;
+    const long long tiles = (probs[k].n + 127) / 128;
+    long long c = tiles;
+    if (total > budget) c = imax64(1, imin64(tiles, tiles * budget / total));
+    at += (int)(tiles == 0 ? 0 : c);
+  }
+  g.block_start[count] = at;
+  return at;
+}
+
+template <int K, int N>
+static int launch_linear_umma_ts_grouped(const peagnn_linear_problem_t* probs, int count, int w_is_out_in, int relu,
+                                         int accumulate, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)2 * (N * K * 4) + (size_t)4 * 32 * (N + 4) * 4 + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(linear_umma_ts_kernel_grouped<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  LinearGroup g;
+  const int blocks = fill_group(probs, count, kNumSMs, g);
+  if (blocks == 0) return PEAGNN_OK;
+  linear_umma_ts_kernel_grouped<K, N><<<blocks, kPipeThreads, smem, stream>>>(g, w_is_out_in, relu, accumulate);
+  return check_launch("peagnn_linear_grouped(umma ts)");
+}
+
+template <int K, int N>
+static int launch_linear_umma_grouped(const peagnn_linear_problem_t* probs, int count, int w_is_out_in, int relu,
+                                      int accumulate, cudaStream_t stream) {
+  constexpr size_t a_bytes = (size_t)2 * (128 * K * 4), stage_bytes = (size_t)8 * 32 * (N / 2 + 4) * 4;
+  constexpr size_t smem = (a_bytes > stage_bytes ? a_bytes : stage_bytes) + (size_t)2 * (N * K * 4) + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(linear_umma_kernel_grouped<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  LinearGroup g;
+  const int blocks = fill_group(probs, count, 2 * kNumSMs, g);
+  if (blocks == 0) return PEAGNN_OK;
+  linear_umma_kernel_grouped<K, N><<<blocks, kUmThreads, smem, stream>>>(g, w_is_out_in, relu, accumulate);
+  return check_launch("peagnn_linear_grouped(umma)");
+}
+
+template <int K, int MT>
+static int launch_linear_tc_grouped(const peagnn_linear_problem_t* probs, int count, int w_is_out_in, int relu,
+                                    int accumulate, cudaStream_t stream) {
+  constexpr int LDXS = (K % 32 == 0) ? K + 16 : K;
+  constexpr size_t smem = ((size_t)2 * (K / 16) * MT * 32 * 4 + (size_t)128 * LDXS) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(linear_tc_kernel_grouped<K, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  LinearGroup g;
+  const int blocks = fill_group(probs, count, 2 * kNumSMs, g);
+  if (blocks == 0) return PEAGNN_OK;
+  linear_tc_kernel_grouped<K, MT><<<blocks, kTcThreads, smem, stream>>>(g, w_is_out_in, relu, accumulate);
+  return check_launch("peagnn_linear_grouped(tc)");
+}
+
+extern "C" int peagnn_linear_grouped(const peagnn_linear_problem_t* problems, int32_t count, int32_t K, int32_t M,
+                                     int w_is_out_in, int relu, int accumulate, peagnn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PEAGNN_REQUIRE(count >= 0 && (problems || count == 0), "peagnn_linear_grouped: null problem list");
+  PEAGNN_REQUIRE(K > 0 && M > 0 && K % 4 == 0 && M % 4 == 0 && K <= 128 && M <= 128,
+                 "peagnn_linear_grouped: K=%d, M=%d must be multiples of 4 in [4, 128]", K, M);
+  for (int k = 0; k < count; ++k) {
+    const peagnn_linear_problem_t& q = problems[k];
+    PEAGNN_REQUIRE(q.n >= 0 && (q.n == 0 || (q.X && q.W && q.Y && q.ldx % 4 == 0 && q.ldy % 4 == 0 && q.ldx >= K && q.ldy >= M)),
+                   "peagnn_linear_grouped: problem %d: bad pointers / leading dimensions", k);
+    PEAGNN_REQUIRE(q.n == 0 || (aligned16(q.X) && aligned16(q.Y) && (!q.bias || aligned16(q.bias)) &&
+                                (!q.out_mask || (aligned16(q.out_mask) && q.ldom % 4 == 0 && q.ldom >= M))),
+                   "peagnn_linear_grouped: problem %d: pointers must be 16-byte aligned", k);
+  }
+  // the shapes of a PEAGNN step under the default kernel choice of peagnn_linear; anything else: one launch per problem
+  const bool ts = dense_mode() >= 3 && K == 64 && M == 64;
+  const bool um = dense_mode() >= 3 && K == 16 && M == 64;
+  const bool tc = dense_mode() >= 3 && K == 64 && M == 16;
+  if (!(ts || um || tc)) {
+    for (int k = 0; k < count; ++k) {
+      const peagnn_linear_problem_t& q = problems[k];
+      const int rc = peagnn_linear(q.X, q.ldx, nullptr, 0, q.n, K, M, q.W, w_is_out_in, q.bias, relu, accumulate, q.Y, q.ldy,
+                                   q.out_mask, q.ldom, stream_);
+      if (rc) return rc;
+    }
+    return PEAGNN_OK;
+  }
+  for (int first = 0; first < count; first += PEAGNN_MAX_GROUP) {
+    const int c = count - first < PEAGNN_MAX_GROUP ? count - first : PEAGNN_MAX_GROUP;
+    int rc;
+    if (ts) rc = launch_linear_umma_ts_grouped<64, 64>(problems + first, c, w_is_out_in, relu, accumulate, stream);
+    else if (um) rc = launch_linear_umma_grouped<16, 64>(problems + first, c, w_is_out_in, relu, accumulate, stream);
+    else rc = launch_linear_tc_grouped<64, 2>(problems + first, c, w_is_out_in, relu, accumulate, stream);
+    if (rc) return rc;
+  }
+  return PEAGNN_OK;
+}
+
 extern "C" size_t peagnn_wgrad_workspace_floats(int64_t n, int32_t K, int32_t M) {
   return (size_t)wgrad_parts(n) * ((size_t)K * M + M) + 64;
 }
@@ -612,6 +720,150 @@ extern "C" int peagnn_linear_wgrad(const float* X, int64_t ldx, const float* dY,
   if (rc) return rc;
   wgrad_finalize_kernel<<<(KM + M + 255) / 256, 256, 0, stream>>>(workspace, parts, K, M, w_is_out_in, dW, db);
   return check_launch("peagnn_linear_wgrad(stage2)");
+}
+
+// ---- grouped weight gradients -----------------------------------------------------------------------------
+struct WgradFinal {
+  int count;
+  int n_parts[PEAGNN_MAX_GROUP];
+  const float* partial[PEAGNN_MAX_GROUP];
+  float* dW[PEAGNN_MAX_GROUP];
+  float* db[PEAGNN_MAX_GROUP];
+};
+// wgrad_finalize_v2_kernel for a group: blockIdx.y = problem; parts folded in CTA order (deterministic)
+__global__ void __launch_bounds__(256) wgrad_finalize_grouped_kernel(const __grid_constant__ WgradFinal f, int K, int M,
+                                                                     int w_is_out_in) {
+  __shared__ float red[256];
+  const int KM = K * M;
+  const int k = blockIdx.y;
+  const float* __restrict__ partial = f.partial[k];
+  const int n_parts = f.n_parts[k];
+  const int o = threadIdx.x & (kFinOutputs - 1), s = threadIdx.x / kFinOutputs;
+  constexpr int SLICES = 256 / kFinOutputs;
+  const int idx = blockIdx.x * kFinOutputs + o;
+  float v = 0.f;
+  if (idx < KM + M) {
+#pragma unroll 4
+    for (int p = s; p < n_parts; p += SLICES) v += partial[(size_t)p * (KM + M) + idx];
+  }
+  red[threadIdx.x] = v;
+  __syncthreads();
+  if (s == 0 && idx < KM + M) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < SLICES; ++q) t += red[q * kFinOutputs + o];
+    if (idx < KM) {
+      if (f.dW[k]) {
+        const int kk = idx / M, m = idx - kk * M;
+        f.dW[k][w_is_out_in ? (size_t)m * K + kk : (size_t)idx] = t;
+      }
+    } else if (f.db[k]) {
+      f.db[k][idx - KM] = t;
+    }
+  }
+}
+
+extern "C" size_t peagnn_wgrad_grouped_workspace_floats(int32_t count, int32_t K, int32_t M) {
+  // every problem gets at least one part; the parts of a launch share a budget of 2 CTAs per SM
+  const size_t per_launch = (size_t)PEAGNN_MAX_GROUP + 2 * kNumSMs;
+  const size_t launches = ((size_t)(count > 0 ? count : 1) + PEAGNN_MAX_GROUP - 1) / PEAGNN_MAX_GROUP;
+  const size_t single = peagnn_wgrad_workspace_floats(1 << 30, K, M);     // the per-problem fallback's need
+  const size_t grouped = launches * per_launch * ((size_t)K * M + M) + 64;
+  return grouped > single ? grouped : single;
+}
+
+template <int K, int M, int ROWS_UNIT, class Launch>
+static int wgrad_grouped_launch(const peagnn_wgrad_problem_t* probs, int count, int w_is_out_in, float* workspace,
+                                cudaStream_t stream, Launch launch, const char* what) {
+  const int KM = K * M;
+  WgradGroup g;
+  WgradFinal f;
+  long long total = 0;
+  for (int k = 0; k < count; ++k) total += (probs[k].n + 255) / 256;
+  const long long budget = 2 * kNumSMs;
+  g.count = f.count = count;
+  int at = 0;
+  for (int k = 0; k < count; ++k) {
+    const long long by_rows = (probs[k].n + 255) / 256;
+    long long c = by_rows;
+    if (total > budget) c = imax64(1, imin64(by_rows, by_rows * budget / total));
+    if (by_rows == 0) c = 0;
+    g.p[k] = probs[k];
+    g.block_start[k] = at;
+    g.rows_per_cta[k] = c ? ((probs[k].n + c - 1) / c + ROWS_UNIT - 1) / ROWS_UNIT * ROWS_UNIT : 0;
+    g.partial[k] = workspace + (size_t)at * (KM + M);
+    f.n_parts[k] = (int)c;
+    f.partial[k] = g.partial[k];
+    f.dW[k] = probs[k].dW;
+    f.db[k] = probs[k].db;
+    at += (int)c;
+  }
+  g.block_start[count] = at;
+  if (at > 0) {
+    launch(g, at);
+    int rc = check_launch(what);
+    if (rc) return rc;
+  }
+  // problems without rows fold zero parts: their outputs are written as zeros
+  wgrad_finalize_grouped_kernel<<<dim3((KM + M + kFinOutputs - 1) / kFinOutputs, count), 256, 0, stream>>>(f, K, M, w_is_out_in);
+  return check_launch("peagnn_linear_wgrad_grouped(stage2)");
+}
+
+extern "C" int peagnn_linear_wgrad_grouped(const peagnn_wgrad_problem_t* problems, int32_t count, int32_t K, int32_t M,
+                                           int w_is_out_in, float* workspace, size_t workspace_floats,
+                                           peagnn_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PEAGNN_REQUIRE(count >= 0 && (problems || count == 0), "peagnn_linear_wgrad_grouped: null problem list");
+  PEAGNN_REQUIRE(K >= 4 && K <= 128 && is_pow2(K) && M >= 4 && M <= 128 && is_pow2(M),
+                 "peagnn_linear_wgrad_grouped: K=%d, M=%d must be powers of two in [4, 128]", K, M);
+  PEAGNN_REQUIRE(workspace && workspace_floats >= peagnn_wgrad_grouped_workspace_floats(count, K, M),
+                 "peagnn_linear_wgrad_grouped: workspace too small");
+  for (int k = 0; k < count; ++k) {
+    const peagnn_wgrad_problem_t& q = problems[k];
+    PEAGNN_REQUIRE(q.n >= 0 && (q.n == 0 || (q.X && q.dY && q.ldx >= K && q.ldd >= M && q.ldx % 4 == 0 && q.ldd % 4 == 0 &&
+                                             aligned16(q.X) && aligned16(q.dY))),
+                   "peagnn_linear_wgrad_grouped: problem %d: bad pointers / leading dimensions / alignment", k);
+  }
+  const bool um = dense_mode() >= 3 && K == 64 && M == 64;
+  const bool tc = dense_mode() >= 3 && K == 64 && M == 16;
+  if (!(um || tc)) {
+    for (int k = 0; k < count; ++k) {
+      const peagnn_wgrad_problem_t& q = problems[k];
+      if (q.n == 0) {
+        if (q.dW) cudaMemsetAsync(q.dW, 0, sizeof(float) * K * M, stream);
+        if (q.db) cudaMemsetAsync(q.db, 0, sizeof(float) * M, stream);
+        continue;
+      }
+      const int rc = peagnn_linear_wgrad(q.X, q.ldx, q.dY, q.ldd, nullptr, 0, q.n, K, M, w_is_out_in, q.dW, q.db, workspace,
+                                         workspace_floats, stream_);
+      if (rc) return rc;
+    }
+    return PEAGNN_OK;
+  }
+  const size_t per_launch = ((size_t)PEAGNN_MAX_GROUP + 2 * kNumSMs) * ((size_t)K * M + M);
+  int launch_no = 0;
+  for (int first = 0; first < count; first += PEAGNN_MAX_GROUP, ++launch_no) {
+    const int c = count - first < PEAGNN_MAX_GROUP ? count - first : PEAGNN_MAX_GROUP;
+    float* ws = workspace + (size_t)launch_no * per_launch;
+    int rc;
+    if (um) {
+      constexpr size_t smem = (size_t)2 * (kUmWgRows / 4) * 144 * (16 + 64 / 8) + 128;
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaFuncSetAttribute(wgrad_umma_kernel_grouped<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+      }
+      rc = wgrad_grouped_launch<64, 64, kUmWgRows>(problems + first, c, w_is_out_in, ws, stream,
+          [&](const WgradGroup& g, int blocks) { wgrad_umma_kernel_grouped<64, 64><<<blocks, kUmThreads, smem, stream>>>(g); },
+          "peagnn_linear_wgrad_grouped(umma)");
+    } else {
+      rc = wgrad_grouped_launch<64, 16, kTcWgRows>(problems + first, c, w_is_out_in, ws, stream,
+          [&](const WgradGroup& g, int blocks) { wgrad_tc_kernel_grouped<64, 16><<<blocks, kTcThreads, 0, stream>>>(g); },
+          "peagnn_linear_wgrad_grouped(tc)");
+    }
+    if (rc) return rc;
+  }
+  return PEAGNN_OK;
 }
 
 extern "C" int peagnn_relu_backward(const float* dy, int64_t ldd, const float* act, int64_t lda, int64_t n,

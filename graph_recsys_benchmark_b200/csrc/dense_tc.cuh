@@ -42,10 +42,10 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 
 // -------------------------------------------------------------------------------------------------
 template <int K, int MT /* n-tiles of 8 columns: M = 8 * MT */>
-__global__ void __launch_bounds__(kTcThreads, 2) linear_tc_kernel(
+__device__ __forceinline__ void linear_tc_kernel_body(
     const float* __restrict__ X, int64_t ldx, int64_t n_rows, const float* __restrict__ W, int w_is_out_in,
     const float* __restrict__ bias, int relu, int accumulate, float* __restrict__ Y, int64_t ldy,
-    const float* __restrict__ out_mask, int64_t ldom) {
+    const float* __restrict__ out_mask, int64_t ldom, const int block_id, const int n_blocks) {
   constexpr int M = 8 * MT;
   constexpr int BM = 128;
   constexpr int K4 = K / 4, KB = K / 16;
@@ -85,9 +85,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) linear_tc_kernel(
     }
   };
 
-  int64_t tile = blockIdx.x;
+  int64_t tile = block_id;
   if (tile < n_tiles) fetch(tile);
-  for (; tile < n_tiles; tile += gridDim.x) {
+  for (; tile < n_tiles; tile += n_blocks) {
     __syncthreads();          // previous tile's readers are done (Wf visible on the first pass)
 #pragma unroll
     for (int j = 0; j < NPRE; ++j) {
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) linear_tc_kernel(
       st4(Xs + r * LDXS + 4 * c, pre[j]);
     }
     __syncthreads();
-    const int64_t next = tile + gridDim.x;
+    const int64_t next = tile + n_blocks;
     if (next < n_tiles) fetch(next);   // in flight while this tile is computed
 
     float acc[MT][4];
@@ -163,6 +163,23 @@ __global__ void __launch_bounds__(kTcThreads, 2) linear_tc_kernel(
   }
 }
 
+template <int K, int MT /* n-tiles of 8 columns: M = 8 * MT */>
+__global__ void __launch_bounds__(kTcThreads, 2) linear_tc_kernel(
+    const float* __restrict__ X, int64_t ldx, int64_t n_rows, const float* __restrict__ W, int w_is_out_in,
+    const float* __restrict__ bias, int relu, int accumulate, float* __restrict__ Y, int64_t ldy,
+    const float* __restrict__ out_mask, int64_t ldom) {
+  linear_tc_kernel_body<K, MT>(X, ldx, n_rows, W, w_is_out_in, bias, relu, accumulate, Y, ldy, out_mask, ldom, (int)blockIdx.x, (int)gridDim.x);
+}
+// grouped form: CTA b works on the problem whose block range holds b, as block (b - first) of (last - first)
+template <int K, int MT /* n-tiles of 8 columns: M = 8 * MT */>
+__global__ void __launch_bounds__(kTcThreads, 2) linear_tc_kernel_grouped(const __grid_constant__ LinearGroup grp, int w_is_out_in, int relu,
+                                                 int accumulate) {
+  const int k = group_of_block(grp, (int)blockIdx.x);
+  const peagnn_linear_problem_t& q = grp.p[k];
+  linear_tc_kernel_body<K, MT>(q.X, q.ldx, q.n, q.W, w_is_out_in, q.bias, relu, accumulate, q.Y, q.ldy, q.out_mask, q.ldom,
+      (int)blockIdx.x - grp.block_start[k], grp.block_start[k + 1] - grp.block_start[k]);
+}
+
 template <int K, int MT>
 static int launch_linear_tc(const float* X, int64_t ldx, int64_t n, const float* W, int w_is_out_in,
                             const float* bias, int relu, int accumulate, float* Y, int64_t ldy,
@@ -185,10 +202,10 @@ static int launch_linear_tc(const float* X, int64_t ldx, int64_t n, const float*
 constexpr int kTcWgRows = 64;
 
 template <int K, int M, bool HAS_MASK>
-__global__ void __launch_bounds__(kTcThreads, 2) wgrad_tc_kernel(
+__device__ __forceinline__ void wgrad_tc_kernel_body(
     const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY, int64_t ldd,
     const float* __restrict__ mask, int64_t ldm, int64_t n_rows, int64_t rows_per_cta,
-    float* __restrict__ partial /* [grid][K*M + M] */) {
+    float* __restrict__ partial /* [parts][K*M + M] */, const int block_id) {
   constexpr int WM = K / 16;                 // warps along dW's rows (one 16-row MMA tile each)
   constexpr int WN = 8 / WM;                 // warps along dW's columns
   constexpr int NT = (M / 8) / WN;           // 8-column tiles per warp
@@ -215,7 +232,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) wgrad_tc_kernel(
 #pragma unroll
   for (int j = 0; j < ND; ++j) bsum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r_begin = (int64_t)block_id * rows_per_cta;
   const int64_t r_end = imin64(n_rows, r_begin + rows_per_cta);
 
   float4 px[NX], pd[ND];
@@ -288,7 +305,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) wgrad_tc_kernel(
       for (int i = 0; i < 4; ++i) { master[j][i] += acc[j][i]; acc[j][i] = 0.f; }
   }
 
-  float* dst = partial + (size_t)blockIdx.x * (KM + M);
+  float* dst = partial + (size_t)block_id * (KM + M);
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     float* p = dst + (size_t)(16 * mt + g) * M + 8 * (nt0 + j) + 2 * t;
@@ -310,6 +327,22 @@ __global__ void __launch_bounds__(kTcThreads, 2) wgrad_tc_kernel(
     for (int r = 0; r < kTcWgRows; ++r) s += Ds[r * LDD + threadIdx.x];
     dst[KM + threadIdx.x] = s;
   }
+}
+
+template <int K, int M, bool HAS_MASK>
+__global__ void __launch_bounds__(kTcThreads, 2) wgrad_tc_kernel(
+    const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY, int64_t ldd,
+    const float* __restrict__ mask, int64_t ldm, int64_t n_rows, int64_t rows_per_cta,
+    float* __restrict__ partial /* [grid][K*M + M] */) {
+  wgrad_tc_kernel_body<K, M, HAS_MASK>(X, ldx, dY, ldd, mask, ldm, n_rows, rows_per_cta, partial, (int)blockIdx.x);
+}
+// grouped form (peagnn_linear_wgrad_grouped): CTA b is part (b - first) of the problem whose block range holds b
+template <int K, int M>
+__global__ void __launch_bounds__(kTcThreads, 2) wgrad_tc_kernel_grouped(const __grid_constant__ WgradGroup grp) {
+  const int k = group_of_block(grp, (int)blockIdx.x);
+  const peagnn_wgrad_problem_t& q = grp.p[k];
+  wgrad_tc_kernel_body<K, M, false>(q.X, q.ldx, q.dY, q.ldd, nullptr, 0, q.n, grp.rows_per_cta[k], grp.partial[k],
+                       (int)blockIdx.x - grp.block_start[k]);
 }
 
 template <int K, int M>

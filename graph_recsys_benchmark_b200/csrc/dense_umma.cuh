@@ -82,10 +82,10 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 }
 
 template <int K, int N>
-__global__ void __launch_bounds__(kUmThreads, 2) linear_umma_kernel(
+__device__ __forceinline__ void linear_umma_kernel_body(
     const float* __restrict__ X, int64_t ldx, int64_t n_rows, const float* __restrict__ W, int w_is_out_in,
     const float* __restrict__ bias, int relu, int accumulate, float* __restrict__ Y, int64_t ldy,
-    const float* __restrict__ out_mask, int64_t ldom) {
+    const float* __restrict__ out_mask, int64_t ldom, const int block_id, const int n_blocks) {
   constexpr int BM = 128;
   constexpr int KC = K / 4;                     // 16-byte chunks along K
   constexpr int KS = K / 8;                     // MMA k-steps
@@ -158,9 +158,9 @@ __global__ void __launch_bounds__(kUmThreads, 2) linear_umma_kernel(
   };
 
   uint32_t phase = 0;
-  int64_t tile = blockIdx.x;
+  int64_t tile = block_id;
   if (tile < n_tiles) fetch(tile);
-  for (; tile < n_tiles; tile += gridDim.x) {
+  for (; tile < n_tiles; tile += n_blocks) {
     // split this tile into A_hi / A_lo (the previous tile's MMAs were waited for by every thread)
 #pragma unroll
     for (int it = 0; it < ITS; ++it) {
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kUmThreads, 2) linear_umma_kernel(
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the MMA
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // orders the previous tile's tcgen05.ld
     __syncthreads();
-    const int64_t next = tile + gridDim.x;
+    const int64_t next = tile + n_blocks;
     if (next < n_tiles) fetch(next);   // in flight while the MMAs and the epilogue run
 
     if (threadIdx.x == 0) {
@@ -248,6 +248,23 @@ __global__ void __launch_bounds__(kUmThreads, 2) linear_umma_kernel(
 }
 
 template <int K, int N>
+__global__ void __launch_bounds__(kUmThreads, 2) linear_umma_kernel(
+    const float* __restrict__ X, int64_t ldx, int64_t n_rows, const float* __restrict__ W, int w_is_out_in,
+    const float* __restrict__ bias, int relu, int accumulate, float* __restrict__ Y, int64_t ldy,
+    const float* __restrict__ out_mask, int64_t ldom) {
+  linear_umma_kernel_body<K, N>(X, ldx, n_rows, W, w_is_out_in, bias, relu, accumulate, Y, ldy, out_mask, ldom, (int)blockIdx.x, (int)gridDim.x);
+}
+// grouped form: CTA b works on the problem whose block range holds b, as block (b - first) of (last - first)
+template <int K, int N>
+__global__ void __launch_bounds__(kUmThreads, 2) linear_umma_kernel_grouped(const __grid_constant__ LinearGroup grp, int w_is_out_in, int relu,
+                                                 int accumulate) {
+  const int k = group_of_block(grp, (int)blockIdx.x);
+  const peagnn_linear_problem_t& q = grp.p[k];
+  linear_umma_kernel_body<K, N>(q.X, q.ldx, q.n, q.W, w_is_out_in, q.bias, relu, accumulate, q.Y, q.ldy, q.out_mask, q.ldom,
+      (int)blockIdx.x - grp.block_start[k], grp.block_start[k + 1] - grp.block_start[k]);
+}
+
+template <int K, int N>
 static int launch_linear_umma(const float* X, int64_t ldx, int64_t n, const float* W, int w_is_out_in,
                               const float* bias, int relu, int accumulate, float* Y, int64_t ldy,
                               const float* out_mask, int64_t ldom, cudaStream_t stream) {
@@ -281,10 +298,10 @@ static int launch_linear_umma(const float* X, int64_t ldx, int64_t n, const floa
 constexpr int kUmWgRows = 64;
 
 template <int K, int M, bool HAS_MASK>
-__global__ void __launch_bounds__(kUmThreads, 2) wgrad_umma_kernel(
+__device__ __forceinline__ void wgrad_umma_kernel_body(
     const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY, int64_t ldd,
     const float* __restrict__ mask, int64_t ldm, int64_t n_rows, int64_t rows_per_cta,
-    float* __restrict__ partial /* [grid][K*M + M] */) {
+    float* __restrict__ partial /* [parts][K*M + M] */, const int block_id) {
   constexpr int KQ = K / 4, MQ = M / 4;                  // column quads of X / dY
   constexpr int KCH = kUmWgRows / 4;                     // 16-byte chunks along the reduction (4 data rows each)
   constexpr uint32_t SBO = 144;                          // 8-feature group pitch
@@ -330,7 +347,7 @@ __global__ void __launch_bounds__(kUmThreads, 2) wgrad_umma_kernel(
   const int xq = threadIdx.x % KQ, xkc = threadIdx.x / KQ;
   const int dq = threadIdx.x % MQ, dkc = threadIdx.x / MQ;
 
-  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r_begin = (int64_t)block_id * rows_per_cta;
   const int64_t r_end = imin64(n_rows, r_begin + rows_per_cta);
 
   float4 px[4], pd[4];
@@ -418,7 +435,7 @@ __global__ void __launch_bounds__(kUmThreads, 2) wgrad_umma_kernel(
   }
 
   // this CTA's partial: thread owns feature 32 * (warp % 4) + lane, columns [col0, col0 + CW)
-  float* dst = partial + (size_t)blockIdx.x * (KM + M);
+  float* dst = partial + (size_t)block_id * (KM + M);
   const int f = 32 * (warp & 3) + lane;
   if (reads_acc && f < K) {
 #pragma unroll
@@ -440,6 +457,22 @@ __global__ void __launch_bounds__(kUmThreads, 2) wgrad_umma_kernel(
   __syncthreads();
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+template <int K, int M, bool HAS_MASK>
+__global__ void __launch_bounds__(kUmThreads, 2) wgrad_umma_kernel(
+    const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY, int64_t ldd,
+    const float* __restrict__ mask, int64_t ldm, int64_t n_rows, int64_t rows_per_cta,
+    float* __restrict__ partial /* [grid][K*M + M] */) {
+  wgrad_umma_kernel_body<K, M, HAS_MASK>(X, ldx, dY, ldd, mask, ldm, n_rows, rows_per_cta, partial, (int)blockIdx.x);
+}
+// grouped form (peagnn_linear_wgrad_grouped): CTA b is part (b - first) of the problem whose block range holds b
+template <int K, int M>
+__global__ void __launch_bounds__(kUmThreads, 2) wgrad_umma_kernel_grouped(const __grid_constant__ WgradGroup grp) {
+  const int k = group_of_block(grp, (int)blockIdx.x);
+  const peagnn_wgrad_problem_t& q = grp.p[k];
+  wgrad_umma_kernel_body<K, M, false>(q.X, q.ldx, q.dY, q.ldd, nullptr, 0, q.n, grp.rows_per_cta[k], grp.partial[k],
+                       (int)blockIdx.x - grp.block_start[k]);
 }
 
 template <int K, int M>
@@ -506,10 +539,10 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 }
 
 template <int K, int N>
-__global__ void __launch_bounds__(kPipeThreads, 1) linear_umma_ts_kernel(
+__device__ __forceinline__ void linear_umma_ts_kernel_body(
     const float* __restrict__ X, int64_t ldx, int64_t n_rows, const float* __restrict__ W, int w_is_out_in,
     const float* __restrict__ bias, int relu, int accumulate, float* __restrict__ Y, int64_t ldy,
-    const float* __restrict__ out_mask, int64_t ldom) {
+    const float* __restrict__ out_mask, int64_t ldom, const int block_id, const int n_blocks) {
   constexpr int BM = 128;
   constexpr int KC = K / 4, KS = K / 8;
   constexpr int KPW = KS / 2;                              // k-steps per producer warp (two warps share a lane quarter)
@@ -566,14 +599,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) linear_umma_ts_kernel(
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
   const uint32_t afull0 = smem_u32(&bars[4]), aempty0 = smem_u32(&bars[6]);
   const int64_t n_tiles = (n_rows + BM - 1) / BM;
-  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t my_tiles = block_id < n_tiles ? (n_tiles - block_id + n_blocks - 1) / n_blocks : 0;
 
   if (warp < kPipeProducerWarps) {
     // ---------------------------------------------------------------- producers: one row (= TMEM lane) per thread
     const int q = warp & 3, h = warp >> 2;
     float4 pre0[2 * KPW], pre1[2 * KPW];
     auto fetch = [&](int64_t i, float4 (&pre)[2 * KPW]) {
-      const int64_t row = (blockIdx.x + i * gridDim.x) * BM + 32 * q + lane;
+      const int64_t row = (block_id + i * n_blocks) * BM + 32 * q + lane;
       const bool ok = i < my_tiles && row < n_rows;
 #pragma unroll
       for (int j = 0; j < 2 * KPW; ++j)
@@ -654,7 +687,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) linear_umma_ts_kernel(
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(aempty0 + 8 * s);
       __syncwarp();
-      const int64_t tile = blockIdx.x + i * gridDim.x;
+      const int64_t tile = block_id + i * n_blocks;
 #pragma unroll
       for (int it = 0; it < 32 / RPI; ++it) {
         const int r = it * RPI + lane / C4;
@@ -683,6 +716,23 @@ __global__ void __launch_bounds__(kPipeThreads, 1) linear_umma_ts_kernel(
   __syncthreads();
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+template <int K, int N>
+__global__ void __launch_bounds__(kPipeThreads, 1) linear_umma_ts_kernel(
+    const float* __restrict__ X, int64_t ldx, int64_t n_rows, const float* __restrict__ W, int w_is_out_in,
+    const float* __restrict__ bias, int relu, int accumulate, float* __restrict__ Y, int64_t ldy,
+    const float* __restrict__ out_mask, int64_t ldom) {
+  linear_umma_ts_kernel_body<K, N>(X, ldx, n_rows, W, w_is_out_in, bias, relu, accumulate, Y, ldy, out_mask, ldom, (int)blockIdx.x, (int)gridDim.x);
+}
+// grouped form: CTA b works on the problem whose block range holds b, as block (b - first) of (last - first)
+template <int K, int N>
+__global__ void __launch_bounds__(kPipeThreads, 1) linear_umma_ts_kernel_grouped(const __grid_constant__ LinearGroup grp, int w_is_out_in, int relu,
+                                                 int accumulate) {
+  const int k = group_of_block(grp, (int)blockIdx.x);
+  const peagnn_linear_problem_t& q = grp.p[k];
+  linear_umma_ts_kernel_body<K, N>(q.X, q.ldx, q.n, q.W, w_is_out_in, q.bias, relu, accumulate, q.Y, q.ldy, q.out_mask, q.ldom,
+      (int)blockIdx.x - grp.block_start[k], grp.block_start[k + 1] - grp.block_start[k]);
 }
 
 template <int K, int N>

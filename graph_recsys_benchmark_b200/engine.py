@@ -27,6 +27,9 @@ _side_streams = {}
 PARALLEL_BRANCHES = True      # False: _Fork runs its branches in order on the current stream (per-kernel timing builds)
 
 
+GROUPED_PROJECTIONS = __import__('os').environ.get('PEAGNN_GROUPED', '1') != '0'   # demand-driven PEAGCN step: one launch per
+                                                                                   # projection shape across the metapaths
+
 N_BRANCHES = int(__import__('os').environ.get('PEAGNN_BRANCHES', '4'))     # side streams per device
 
 
@@ -63,6 +66,19 @@ class _Fork(object):
             import contextlib
             return contextlib.nullcontext()
         return torch.cuda.stream(self.streams[k % len(self.streams)])
+
+    def record(self):
+        """An event on the current branch (None when the branches run in order on one stream)."""
+        if not self.parallel:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return ev
+
+    def wait(self, ev):
+        """The current branch continues after ``ev`` (a cross-branch dependency)."""
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
 
     def __exit__(self, *exc):
         if self.parallel:
@@ -349,7 +365,13 @@ class _GcnBody(torch.autograd.Function):
         wide = P * D
         t2 = torch.empty(n, wide, dtype=torch.float32, device=dev)
         h1 = [torch.empty(n, H, dtype=torch.float32, device=dev) for _ in range(P)]
-        with _Fork(dev) as fork:                               # the per-metapath chains are independent: parallel branches
+        if GROUPED_PROJECTIONS:                                # one launch per projection shape across the metapaths
+            rel = plan.rel_of_path
+            F_.linear_grouped_raw([(A1[rel[p]], W1[p], b1[p], h1[p], None) for p in range(P)], plan.emb, H, False, relu=True)
+            F_.linear_grouped_raw([(h1[p], W2[p], None, t2[:, plan.slot[p] * D:(plan.slot[p] + 1) * D], None) for p in range(P)],
+                                  H, D, False)
+        else:
+          with _Fork(dev) as fork:                             # the per-metapath chains are independent: parallel branches
             for p in range(P):
                 r, s = plan.rel_of_path[p], plan.slot[p]
                 with fork.on(r):
@@ -406,8 +428,32 @@ class _GcnBody(torch.autograd.Function):
                 dA1[r] = new(n, E)
                 first_of[r] = p
         n_branches = len(fork_streams(dev))
-        dp1 = [new(n, H) for _ in range(min(P, n_branches))]   # one gated-gradient buffer per branch
-        with _Fork(dev) as fork:
+        if GROUPED_PROJECTIONS:
+            rel = plan.rel_of_path
+            dslot = lambda p: dt2[:, plan.slot[p] * D:(plan.slot[p] + 1) * D]
+            dp1 = [new(n, H) for _ in range(P)]
+            rounds, seen = [], {}
+            for p in range(P):                                 # metapaths that share d A1[r]: successive launches, fixed order
+                k = seen.get(rel[p], 0)
+                seen[rel[p]] = k + 1
+                while len(rounds) <= k:
+                    rounds.append([])
+                rounds[k].append(p)
+            with _Fork(dev) as fork:
+                with fork.on(0):                               # d P1 = (d T2 W2^T) gated by relu -> d A1
+                    F_.linear_grouped_raw([(dslot(p), W2[p], None, dp1[p], h1[p]) for p in range(P)], D, H, True)
+                    have_dp1 = fork.record()
+                    for k, members in enumerate(rounds):
+                        F_.linear_grouped_raw([(dp1[p], W1[p], None, dA1[rel[p]], None) for p in members], H, E, True,
+                                              accumulate=k > 0)
+                with fork.on(1):                               # d W2 needs nothing of the above; d W1, d b1 need d P1
+                    F_.wgrad_grouped_raw([(h1[p], dslot(p), dW2[p], None) for p in range(P)], H, D, False)
+                    fork.wait(have_dp1)
+                    F_.wgrad_grouped_raw([(A1[rel[p]], dp1[p], dW1[p], db1[p]) for p in range(P)], E, H, False)
+            del dp1
+        else:
+          dp1 = [new(n, H) for _ in range(min(P, n_branches))]   # one gated-gradient buffer per branch
+          with _Fork(dev) as fork:
             for p in range(P):
                 r, s = plan.rel_of_path[p], plan.slot[p]
                 with fork.on(r):                               # metapaths sharing dA1[r] stay on one branch, in order
@@ -466,7 +512,26 @@ class _GcnBodyLean(torch.autograd.Function):
             h1r = [torch.empty(max(ranges[p][1] - ranges[p][0], 0), H, dtype=torch.float32, device=dev) for p in range(P)]
             h1c = [torch.empty(nl, H, dtype=torch.float32, device=dev) for p in range(P)]
         t2c = torch.empty(nl, wide, dtype=torch.float32, device=dev)
-        with _Fork(dev) as fork:
+        if GROUPED_PROJECTIONS:
+            # every metapath's range and list problems of one shape as ONE launch (peagnn_linear_grouped): 26 problems of
+            # 12 k - 160 k rows pay one prologue / tail together instead of 26, on one stream
+            slot = lambda t, p, a, b: t[a:b, plan.slot[p] * D:(plan.slot[p] + 1) * D]
+            rel = plan.rel_of_path
+            has = [p for p in range(P) if ranges[p][1] > ranges[p][0]]
+            with _Fork(dev) as fork:                           # the range chain and the list chain are independent
+                with fork.on(0):
+                    if pre is None:
+                        F_.linear_grouped_raw([(A1[rel[p]][ranges[p][0]:ranges[p][1]], W1[p], b1[p], h1r[p], None) for p in has],
+                                              plan.emb, H, False, relu=True)
+                    F_.linear_grouped_raw([(h1r[p], W2[p], None, slot(t2, p, ranges[p][0], ranges[p][1]), None) for p in has],
+                                          H, D, False)
+                with fork.on(1):
+                    if pre is None:
+                        F_.linear_grouped_raw([(a1c[rel[p]], W1[p], b1[p], h1c[p], None) for p in range(P)], plan.emb, H, False,
+                                              relu=True)
+                    F_.linear_grouped_raw([(h1c[p], W2[p], None, slot(t2c, p, 0, nl), None) for p in range(P)], H, D, False)
+        else:
+          with _Fork(dev) as fork:
             for p in range(P):
                 r, s = plan.rel_of_path[p], plan.slot[p]
                 lo, hi = ranges[p]
@@ -547,7 +612,42 @@ class _GcnBodyLean(torch.autograd.Function):
         dW2b, dW1b, db1b = [new(H, D) for _ in range(P)], [new(E, H) for _ in range(P)], [new(H) for _ in range(P)]
         dp1r = [new(max(ranges[p][1] - ranges[p][0], 0), H) for p in range(P)]
         dp1c, dac = [new(nl, H) for _ in range(P)], [new(nl, E) for _ in range(P)]
-        with _Fork(dev) as fork:
+        if GROUPED_PROJECTIONS:
+            rel = plan.rel_of_path
+            has = [p for p in range(P) if ranges[p][1] > ranges[p][0]]
+            dslot = lambda p: dt2[ranges[p][0]:ranges[p][1], plan.slot[p] * D:(plan.slot[p] + 1) * D]
+            a1r = lambda p: A1[rel[p]][ranges[p][0]:ranges[p][1]]
+            rounds, seen = [], {}
+            for p in has:                                      # metapaths that share d A1[r]: successive launches, fixed order
+                k = seen.get(rel[p], 0)
+                seen[rel[p]] = k + 1
+                while len(rounds) <= k:
+                    rounds.append([])
+                rounds[k].append(p)
+            tc = lambda p: dt2c[:, plan.slot[p], :]
+            with _Fork(dev) as fork:                           # four independent chains of grouped launches
+                with fork.on(0):                               # range: d P1 = (d T2 W2^T) gated by relu -> d A1
+                    F_.linear_grouped_raw([(dslot(p), W2[p], None, dp1r[p], h1r[p]) for p in has], D, H, True)
+                    have_dp1r = fork.record()
+                    for members in rounds:
+                        F_.linear_grouped_raw([(dp1r[p], W1[p], None, dA1[rel[p]][ranges[p][0]:ranges[p][1]], None)
+                                               for p in members], H, E, True, accumulate=True)
+                with fork.on(1):                               # range: d W2 (a metapath without a range pass gets zeros),
+                    F_.wgrad_grouped_raw([(h1r[p], dslot(p), dW2a[p], None) for p in range(P)], H, D, False)
+                    fork.wait(have_dp1r)                       # ... then d W1, d b1 next to the d A1 launches
+                    F_.wgrad_grouped_raw([(a1r(p), dp1r[p], dW1a[p], db1a[p]) for p in range(P)], E, H, False)
+                with fork.on(2):                               # list: the same on the gathered batch rows
+                    F_.linear_grouped_raw([(tc(p), W2[p], None, dp1c[p], h1c[p]) for p in range(P)], D, H, True)
+                    have_dp1c = fork.record()
+                    F_.linear_grouped_raw([(dp1c[p], W1[p], None, dac[p], None) for p in range(P)], H, E, True)
+                with fork.on(3):
+                    F_.wgrad_grouped_raw([(h1c[p], tc(p), dW2b[p], None) for p in range(P)], H, D, False)
+                    fork.wait(have_dp1c)
+                    F_.wgrad_grouped_raw([(a1c[rel[p]], dp1c[p], dW1b[p], db1b[p]) for p in range(P)], E, H, False)
+            for p in range(P):
+                dA1[rel[p]].index_add_(0, ids, dac[p])         # masked-out entries add exact zeros: order-independent
+        else:
+          with _Fork(dev) as fork:
             for p in range(P):
                 r, s = plan.rel_of_path[p], plan.slot[p]
                 lo, hi = ranges[p]

@@ -165,6 +165,44 @@ def active_rows(ids, n_nodes):
     return ActiveRows(mark_rows(flat, n_nodes), srt, first)
 
 
+def merge_ranges(ranges):
+    """Sorted, disjoint form of a list of [lo, hi) id ranges (overlapping / touching ranges are joined)."""
+    out = []
+    for lo, hi in sorted((int(lo), int(hi)) for lo, hi in ranges if hi > lo):
+        if out and lo <= out[-1][1]:
+            out[-1] = (out[-1][0], max(out[-1][1], hi))
+        else:
+            out.append((lo, hi))
+    return out
+
+
+class RowSets(object):
+    """Rows a row-wise op of a demand-driven step has to produce: a few node-id ranges (node types, static) plus the
+    batch rows (``active``: sorted ids with duplicates, a fixed-size list).  ``keep()`` marks the list entries that
+    stand for a row not yet covered - first occurrence of the id, outside every range - so gradients count each
+    row once."""
+
+    def __init__(self, ranges, active):
+        self.ranges, self.active = merge_ranges(ranges), active
+        self.ids = active.ids
+
+    def keep(self):
+        cache = getattr(self.active, '_keep', None)
+        if cache is None:
+            cache = self.active._keep = {}
+        key = tuple(self.ranges)
+        k = cache.get(key)
+        if k is None:
+            k = self.active.first
+            for lo, hi in self.ranges:
+                k = k & ((self.ids < lo) | (self.ids >= hi))
+            cache[key] = k
+        return k
+
+    def n_rows(self):
+        return sum(hi - lo for lo, hi in self.ranges) + int(self.ids.numel())
+
+
 class _GatherActive(torch.autograd.Function):
     """rows ``active.ids`` of a table whose gradient is wanted once per node: forward = index_select, backward = the
     list gradient added back into a zero table (later occurrences of a node carry exact zeros upstream)."""
@@ -216,13 +254,11 @@ def column_sum_where_nonzero(dout, active=None, needed=None):
         rows = dout.index_select(0, active.ids) * active.first[:, None].to(dout.dtype)
         wgrad_raw(None, rows, 0, M, 0, None, out)
         return out
-    if needed is not None and needed.range is not None and needed.active is not None and needed.active.ids is not None:
-        lo, hi = needed.range
-        a = needed.active
-        keep = a.first & ((a.ids < lo) | (a.ids >= hi))
-        rows = dout.index_select(0, a.ids) * keep[:, None].to(dout.dtype)
+    if needed is not None and needed.ranges is not None and needed.active is not None and needed.active.ids is not None:
+        sets = RowSets(needed.ranges, needed.active)
+        rows = dout.index_select(0, sets.ids) * sets.keep()[:, None].to(dout.dtype)
         wgrad_raw(None, rows, 0, M, 0, None, out)
-        if hi > lo:
+        for lo, hi in sets.ranges:
             part = torch.empty_like(out)
             wgrad_raw(None, dout[lo:hi], 0, M, 0, None, part)
             out.add_(part)
@@ -272,6 +308,49 @@ def wgrad_raw(X, dY, K, M, w_is_out_in, dW, db, mask=None):
         _lib.call('peagnn_linear_wgrad', _ptr(X), X.stride(0) if X is not None else 0, _ptr(dY), dY.stride(0),
                   _ptr(mask), mask.stride(0) if mask is not None else 0, n, K, M, int(w_is_out_in),
                   _ptr(dW), _ptr(db), _ptr(ws), need, _stream(), tag=tag, nbytes=nbytes)
+
+
+def linear_grouped_raw(problems, K, M, w_is_out_in, relu=False, accumulate=False):
+    """``peagnn_linear_grouped``: the projections ``(X, W, bias, out, out_mask)`` of ONE shape as a single launch (the
+    per-metapath projections of a step: many small problems).  Outputs must not overlap."""
+    problems = [q for q in problems if q[0].shape[0] > 0]
+    if not problems:
+        return
+    arr = (_lib.LinearProblem * len(problems))()
+    nbytes = 0
+    for k, (X, W, bias, out, out_mask) in enumerate(problems):
+        assert X.shape[1] == K and out.shape[1] == M and out.shape[0] == X.shape[0]
+        a = arr[k]
+        a.X, a.ldx, a.n, a.W, a.bias = X.data_ptr(), X.stride(0), X.shape[0], W.data_ptr(), (bias.data_ptr() if bias is not None else None)
+        a.Y, a.ldy = out.data_ptr(), out.stride(0)
+        a.out_mask, a.ldom = (out_mask.data_ptr(), out_mask.stride(0)) if out_mask is not None else (None, 0)
+        nbytes += linear_algorithmic_bytes(X.shape[0], K, M, accumulate, out_mask is not None)
+    dev = problems[0][0].device
+    with _on(dev):
+        _lib.call('peagnn_linear_grouped', C.cast(arr, C.c_void_p), len(problems), K, M, int(w_is_out_in), int(relu),
+                  int(accumulate), _stream(), tag='linear_%dto%d_grouped' % (K, M) if _lib.profile is not None else None,
+                  nbytes=nbytes)
+
+
+def wgrad_grouped_raw(problems, K, M, w_is_out_in):
+    """``peagnn_linear_wgrad_grouped``: the weight (and bias) gradients ``(X, dY, dW, db)`` of ONE shape as two launches.
+    A problem without rows gets zeros."""
+    if not problems:
+        return
+    arr = (_lib.WgradProblem * len(problems))()
+    nbytes = 0
+    for k, (X, dY, dW, db) in enumerate(problems):
+        assert X.shape[1] == K and dY.shape[1] == M and X.shape[0] == dY.shape[0]
+        a = arr[k]
+        a.X, a.ldx, a.dY, a.ldd, a.n = X.data_ptr(), X.stride(0), dY.data_ptr(), dY.stride(0), X.shape[0]
+        a.dW, a.db = (dW.data_ptr() if dW is not None else None), (db.data_ptr() if db is not None else None)
+        nbytes += 4 * X.shape[0] * (K + M) + 4 * K * M
+    dev = problems[0][0].device
+    need = int(_lib.query('peagnn_wgrad_grouped_workspace_floats', len(problems), K, M))
+    ws = _ws(need, dev)
+    with _on(dev):
+        _lib.call('peagnn_linear_wgrad_grouped', C.cast(arr, C.c_void_p), len(problems), K, M, int(w_is_out_in), _ptr(ws),
+                  need, _stream(), tag='wgrad_%dx%d_grouped' % (K, M) if _lib.profile is not None else None, nbytes=nbytes)
 
 
 def relu_backward_raw(dy, act):
@@ -457,9 +536,9 @@ class NeededRows(object):
     """Rows of an intermediate step's output that the rest of a demand-driven loss() reads: ``static`` (a bitmap fixed
     by the metapath: the node-id range of the next relation's sources) OR the step's batch rows -> ``bitmap``."""
 
-    def __init__(self, static, bitmap, range=None, active=None):
+    def __init__(self, static, bitmap, ranges=None, active=None):
         self.static, self.bitmap = static, bitmap
-        self.range, self.active = range, active      # (lo, hi) of the static part when it is one id range; the batch rows
+        self.ranges, self.active = ranges, active    # the static part as disjoint id ranges [(lo, hi)]; the batch rows
 
     def covers(self, csr):
         """True when every row of ``csr`` that has an edge is marked by the static part (decided once per structure,

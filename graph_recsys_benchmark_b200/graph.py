@@ -305,6 +305,14 @@ class RelationGraph(object):
     def nnz(self):
         return self.fwd.nnz
 
+    def source_range(self):
+        """[lo, hi) node-id range holding every source of the relation (ids are contiguous by type upstream,
+        datasets/movielens.py:184-227: this is the source type's range; one host sync, at first use)."""
+        if getattr(self, '_src_range', None) is None:
+            col = self.fwd.col
+            self._src_range = (int(col.min().item()), int(col.max().item()) + 1) if col.numel() else (0, 0)
+        return self._src_range
+
     def _scale(self, csr, add, power, clamp):
         out = torch.empty(self.num_nodes, dtype=torch.float32, device=csr.rowptr.device)
         with _on(out.device):

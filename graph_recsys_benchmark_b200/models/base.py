@@ -129,26 +129,27 @@ class PEABaseChannel(torch.nn.Module):
         cache = getattr(active, '_needed', None)
         if cache is None:
             cache = active._needed = {}
-        later = active.bitmap                               # bitmap of the rows read of step s+1's output
+        statics = getattr(self, '_static_bitmaps', None)
+        if statics is None:
+            statics = self._static_bitmaps = {}
+        ranges = []                                         # static part of the rows read of step s+1's output
         for s in range(S - 2, -1, -1):
             if not getattr(layers[s], 'supports_needed', False):
                 break
             g_next = get_graph(edge_index_list[s + 1], n, keep_self_loops=getattr(layers[s + 1], 'keeps_self_loops', False))
-            hit = getattr(g_next, '_source_range_bitmap', None)
-            if hit is None:
-                col = g_next.fwd.col
-                lo, hi = (int(col.min().item()), int(col.max().item()) + 1) if col.numel() else (0, 0)
-                hit = g_next._source_range_bitmap = ((lo, hi), F_.range_bitmap(lo, hi, n, active.device))
-            rng, static = hit
-            key = (id(static), id(later))
+            ranges = F_.merge_ranges(ranges + [g_next.source_range()])
+            key = tuple(ranges)
+            static = statics.get(key)
+            if static is None:
+                static = F_.range_bitmap(0, 0, n, active.device)
+                for lo, hi in ranges:
+                    static = torch.bitwise_or(static, F_.range_bitmap(lo, hi, n, active.device))
+                statics[key] = static
             bm = cache.get(key)
             if bm is None:
-                bm = cache[key] = torch.bitwise_or(static, later)   # shared by the channels with the same later steps
-            # (range, batch rows) describe the marked rows exactly only right below the last step
-            out[s] = F_.NeededRows(static, bm, rng if s == S - 2 else None, active if s == S - 2 else None)
-            later = bm
+                bm = cache[key] = torch.bitwise_or(static, active.bitmap)   # shared by the channels with the same later steps
+            out[s] = F_.NeededRows(static, bm, ranges, active)
         return out
-
 
 class PEABaseRecsysModel(GraphRecsysModel):
     def __init__(self, **kwargs):

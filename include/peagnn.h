@@ -213,6 +213,27 @@ int peagnn_linear(const float* X, int64_t ldx, const float* mask, int64_t ldm, i
                   int relu, int accumulate, float* Y, int64_t ldy, const float* out_mask,
                   int64_t ldom, peagnn_stream_t stream);
 
+/* One projection problem of a grouped launch (same meaning as the arguments of peagnn_linear; no input gate). */
+typedef struct {
+  const float* X;
+  int64_t ldx;
+  int64_t n;                 /* rows; 0 = nothing to do */
+  const float* W;
+  const float* bias;         /* may be NULL */
+  float* Y;
+  int64_t ldy;
+  const float* out_mask;     /* may be NULL */
+  int64_t ldom;
+} peagnn_linear_problem_t;
+#define PEAGNN_MAX_GROUP 32
+/* `count` (<= PEAGNN_MAX_GROUP) independent projections of ONE shape (K, M, weight layout, relu, accumulate) as a single
+ * launch: the per-metapath projections of a step (models/base.py:137-139 runs them one conv at a time) are many small
+ * problems - 13 x 12 k rows - whose launches each pay a prologue (weight split into shared memory, TMEM allocation) and
+ * a tail; grouped, every CTA still works on one problem, but all of them are resident together.  Outputs must not
+ * overlap between problems.  Shapes without a grouped kernel run as `count` single launches. */
+int peagnn_linear_grouped(const peagnn_linear_problem_t* problems, int32_t count, int32_t K, int32_t M,
+                          int w_is_out_in, int relu, int accumulate, peagnn_stream_t stream);
+
 /* Floats of workspace for peagnn_linear_wgrad. */
 size_t peagnn_wgrad_workspace_floats(int64_t num_rows, int32_t K, int32_t M);
 /* dW = X^T @ (dY * (mask > 0)) stored as [K, M] (or [M, K] if w_is_out_in), db[m] = column sums
@@ -222,6 +243,24 @@ int peagnn_linear_wgrad(const float* X, int64_t ldx, const float* dY, int64_t ld
                         const float* mask, int64_t ldm, int64_t num_rows, int32_t K, int32_t M,
                         int w_is_out_in, float* dW, float* db, float* workspace,
                         size_t workspace_floats, peagnn_stream_t stream);
+
+/* One weight-gradient problem of a grouped launch (arguments of peagnn_linear_wgrad; no gate). */
+typedef struct {
+  const float* X;
+  int64_t ldx;
+  const float* dY;
+  int64_t ldd;
+  int64_t n;                 /* rows; 0: dW / db are set to zero */
+  float* dW;                 /* may be NULL */
+  float* db;                 /* may be NULL */
+} peagnn_wgrad_problem_t;
+/* `count` (<= PEAGNN_MAX_GROUP per launch; longer lists are cut) weight gradients of ONE shape as two launches
+ * (partial sums per CTA, then one fold per problem in CTA order: deterministic).  Workspace >=
+ * peagnn_wgrad_grouped_workspace_floats(count, K, M) floats. */
+size_t peagnn_wgrad_grouped_workspace_floats(int32_t count, int32_t K, int32_t M);
+int peagnn_linear_wgrad_grouped(const peagnn_wgrad_problem_t* problems, int32_t count, int32_t K, int32_t M,
+                                int w_is_out_in, float* workspace, size_t workspace_floats,
+                                peagnn_stream_t stream);
 
 /* y = dy * (act > 0), elementwise over a [num_rows, feat] block (relu backward). */
 int peagnn_relu_backward(const float* dy, int64_t ldd, const float* act, int64_t lda,

@@ -521,3 +521,69 @@ def test_gat_step_on_the_rows_the_next_step_reads(gname, covering, fout):
     finally:
         pgraph.HEAVY_THRESHOLD, pgraph.CHUNK_EDGES = old
         pgraph.clear_cache()
+
+
+@pytest.mark.parametrize('K,M,out_in', [(64, 64, False), (64, 16, False), (16, 64, True), (64, 64, True), (32, 32, False)])
+@pytest.mark.parametrize('count', [1, 13, 40])
+def test_grouped_projections_equal_single_launches(K, M, out_in, count):
+    """peagnn_linear_grouped: many problems of one shape in one launch (row counts from 0 to several tiles, strided
+    outputs, bias / relu, the relu-backward gate on the way out, accumulation) - the same tiles through the same kernel
+    body as peagnn_linear, so the results are bit-identical; (32, 32) has no grouped kernel and runs as single launches;
+    40 problems are cut into two launches."""
+    from graph_recsys_benchmark_b200 import functional as F_
+    torch.manual_seed(K + M + count)
+    rows = [0, 1, 127, 128, 129, 700, 3000, 5000, 12288]
+    for relu, accumulate, gated in ((True, False, False), (False, True, False), (False, False, True)):
+        probs, want = [], []
+        for k in range(count):
+            n = rows[(k * 5 + count) % len(rows)]
+            X = torch.randn(n, K, device=DEV)
+            W = torch.randn((M, K) if out_in else (K, M), device=DEV) * 0.3
+            bias = torch.randn(M, device=DEV) if (k % 2 == 0 and not gated) else None
+            wide = torch.randn(n, 2 * M, device=DEV)                    # the output is a column slice: leading dimension 2M
+            out = wide[:, M:]
+            gate = torch.randn(n, M, device=DEV) if gated else None
+            ref = out.clone()
+            if n:
+                F_.linear_raw(X, W, ref, out_in, bias, relu, accumulate, out_mask=gate)
+            probs.append((X, W, bias, out, gate))
+            want.append(ref)
+        F_.linear_grouped_raw(probs, K, M, out_in, relu=relu, accumulate=accumulate)
+        for (X, W, bias, out, gate), ref in zip(probs, want):
+            if K == 64 and M == 64 and 0 < X.shape[0] < 4096:
+                # a single 64 -> 64 launch below 4096 rows takes the SS-form kernel, the group always the TS form
+                assert rel_err(out, ref) < 2e-6
+            else:
+                assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize('K,M', [(64, 64), (64, 16), (16, 64)])
+@pytest.mark.parametrize('count', [1, 26, 35])
+def test_grouped_weight_gradients(K, M, count):
+    """peagnn_linear_wgrad_grouped against fp64: d W = X^T d Y and d b = column sums per problem; a problem without rows
+    gets zeros; run twice: bit-identical (fixed fold order)."""
+    from graph_recsys_benchmark_b200 import functional as F_
+    torch.manual_seed(K * M + count)
+    rows = [0, 5, 256, 257, 1000, 4096, 12288, 20000]
+    probs, want = [], []
+    for k in range(count):
+        n = rows[(k * 3 + count) % len(rows)]
+        wide = torch.randn(n, K + 16, device=DEV)
+        X = wide[:, :K] if K + 16 != K else wide                          # strided input (leading dimension K + 16)
+        dY = torch.randn(n, M, device=DEV)
+        dW = torch.full((K, M), 7.0, device=DEV)
+        db = torch.full((M,), 7.0, device=DEV) if k % 2 == 0 else None
+        probs.append((X, dY, dW, db))
+        want.append((X.double().t() @ dY.double(), dY.double().sum(0)))
+    F_.wgrad_grouped_raw(probs, K, M, False)
+    first = [(q[2].clone(), q[3].clone() if q[3] is not None else None) for q in probs]
+    for (X, dY, dW, db), (w, b) in zip(probs, want):
+        if X.shape[0] == 0:
+            assert float(dW.abs().max()) == 0. and (db is None or float(db.abs().max()) == 0.)
+            continue
+        assert rel_err(dW, w) < TOL
+        if db is not None:
+            assert rel_err(db, b) < TOL
+    F_.wgrad_grouped_raw(probs, K, M, False)
+    for (X, dY, dW, db), (w0, b0) in zip(probs, first):
+        assert torch.equal(dW, w0) and (db is None or torch.equal(db, b0))

@@ -359,7 +359,10 @@ def test_demand_driven_loss_equals_full_propagation(kind, entity_aware, shape):
     assert abs(lean.item() - full.item()) <= 2e-6 * abs(full.item())
     for n, p in model.named_parameters():
         if float(ref_grads[n].abs().max()) > 1e-12:
-            assert rel_err(p.grad, ref_grads[n]) < 1e-5, n
+            # two fp32 evaluations of the same sums in different orders (a bias gradient is summed over the [3B] batch rows
+            # here, over all N rows - mostly zeros - there; observed up to 2.1e-5 on the ML-small GAT biases).  Each of the
+            # two is judged against the reference's fp64 run on its own in tests/test_gpu_reference_fixtures.py
+            assert rel_err(p.grad, ref_grads[n]) < 5e-5, n
     # and it is reproducible run to run
     model.zero_grad()
     again = model.loss(batch)
