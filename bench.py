@@ -653,9 +653,9 @@ def product_train(c):
         }
     if proj:
         line['roofline_projection'] = {
-            'bound': 'hbm', 'kernel': 'linear_umma / linear_tc / wgrad_umma / wgrad_tc (peagnn_linear, peagnn_linear_wgrad)',
+            'bound': 'hbm', 'kernel': 'linear_umma_ts / linear_umma / linear_tc / wgrad_umma / wgrad_tc, grouped across the metapaths where the step allows (peagnn_linear[_grouped], peagnn_linear_wgrad[_grouped])',
             'achieved': proj['gbs'], 'peak': c['hbm_peak'], 'unit': 'GB/s', 'frac': proj['gbs'] / c['hbm_peak'],
-            'bytes': '4 N (K + M) + 4 K M per launch (+ 4 N M when accumulating / gating)', 'traffic': None,
+            'bytes': '4 N (K + M) + 4 K M per problem (+ 4 N M when accumulating / gating), summed over the problems of a grouped launch', 'traffic': None,
             'launches_per_step': proj['launches_per_step'], 'ms_per_step': proj['ms_per_step'],
             'share_of_step': proj['ms_per_step'] / ms_roof if ms_roof else None,
         }
