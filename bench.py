@@ -331,8 +331,16 @@ def dominant_launch(fam, hbm_peak, gather):
     it with the small, latency-bound relations)."""
     name, (cnt, nb, ms) = max(fam['by_name'].items(), key=lambda kv: kv[1][1] / kv[1][0])
     gbs = nb / (ms * 1e-3) / 1e9 if ms > 0 else None
-    return {'tag': name, 'launches': cnt, 'bytes_per_launch': nb / cnt, 'ms_per_launch': ms / cnt, 'achieved': gbs,
-            'frac': gbs / hbm_peak if gbs else None, 'frac_of_l2_gather_ceiling': (gbs / gather['gbs']) if (gbs and gather) else None}
+    out = {'tag': name, 'launches': cnt, 'bytes_per_launch': nb / cnt, 'ms_per_launch': ms / cnt, 'achieved': gbs,
+           'frac': gbs / hbm_peak if gbs else None, 'frac_of_l2_gather_ceiling': (gbs / gather['gbs']) if (gbs and gather) else None}
+    import re
+    m = re.search(r'_f(\d+)_e(\d+)_n(\d+)', name)
+    if m:
+        # SURVEY 8(d): what HAS to cross HBM once when the gathered table stays in L2 - the index stream, the gathered
+        # table and the output table: E*4 + N*(F_g + F_o)*4 + (N+1)*4; `traffic` (ncu dram bytes) is to be read against this
+        F, E, N = (int(v) for v in m.groups())
+        out['compulsory_bytes_per_launch'] = E * 4 + N * (F + F) * 4 + (N + 1) * 4
+    return out
 
 
 def measure_gather_ceiling(model, ds, dev):

@@ -583,6 +583,7 @@ class ShardedGcnPlan(object):
         self.order_t = torch.tensor(self.order, dtype=torch.long, device=model.x.device)
         first = model.pea_channels[0].gnn_layers
         self.emb, self.hidden, self.repr = first[0].in_channels, first[0].out_channels, first[1].out_channels
+        self.grouped_shapes = (self.emb, self.hidden, self.repr) == (64, 64, 16)
         self._table = self._dtab = None
         self._xbuf = {}
 

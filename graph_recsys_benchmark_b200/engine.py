@@ -125,6 +125,9 @@ class GcnPlan(object):
         self.order_t = torch.tensor(self.order, dtype=torch.long, device=model.x.device)
         first = model.pea_channels[0].gnn_layers
         self.emb, self.hidden, self.repr = first[0].in_channels, first[0].out_channels, first[1].out_channels
+        # the shapes the grouped projection kernels exist for (every shipped configuration); any other width keeps the
+        # single launches on parallel branches
+        self.grouped_shapes = (self.emb, self.hidden, self.repr) == (64, 64, 16)
         self._src_range = None
 
     def source_range_tensors(self, dev):
@@ -365,7 +368,7 @@ class _GcnBody(torch.autograd.Function):
         wide = P * D
         t2 = torch.empty(n, wide, dtype=torch.float32, device=dev)
         h1 = [torch.empty(n, H, dtype=torch.float32, device=dev) for _ in range(P)]
-        if GROUPED_PROJECTIONS:                                # one launch per projection shape across the metapaths
+        if GROUPED_PROJECTIONS and plan.grouped_shapes:                                # one launch per projection shape across the metapaths
             rel = plan.rel_of_path
             F_.linear_grouped_raw([(A1[rel[p]], W1[p], b1[p], h1[p], None) for p in range(P)], plan.emb, H, False, relu=True)
             F_.linear_grouped_raw([(h1[p], W2[p], None, t2[:, plan.slot[p] * D:(plan.slot[p] + 1) * D], None) for p in range(P)],
@@ -428,7 +431,7 @@ class _GcnBody(torch.autograd.Function):
                 dA1[r] = new(n, E)
                 first_of[r] = p
         n_branches = len(fork_streams(dev))
-        if GROUPED_PROJECTIONS:
+        if GROUPED_PROJECTIONS and plan.grouped_shapes:
             rel = plan.rel_of_path
             dslot = lambda p: dt2[:, plan.slot[p] * D:(plan.slot[p] + 1) * D]
             dp1 = [new(n, H) for _ in range(P)]
@@ -512,7 +515,7 @@ class _GcnBodyLean(torch.autograd.Function):
             h1r = [torch.empty(max(ranges[p][1] - ranges[p][0], 0), H, dtype=torch.float32, device=dev) for p in range(P)]
             h1c = [torch.empty(nl, H, dtype=torch.float32, device=dev) for p in range(P)]
         t2c = torch.empty(nl, wide, dtype=torch.float32, device=dev)
-        if GROUPED_PROJECTIONS:
+        if GROUPED_PROJECTIONS and plan.grouped_shapes:
             # every metapath's range and list problems of one shape as ONE launch (peagnn_linear_grouped): 26 problems of
             # 12 k - 160 k rows pay one prologue / tail together instead of 26, on one stream
             slot = lambda t, p, a, b: t[a:b, plan.slot[p] * D:(plan.slot[p] + 1) * D]
@@ -612,7 +615,7 @@ class _GcnBodyLean(torch.autograd.Function):
         dW2b, dW1b, db1b = [new(H, D) for _ in range(P)], [new(E, H) for _ in range(P)], [new(H) for _ in range(P)]
         dp1r = [new(max(ranges[p][1] - ranges[p][0], 0), H) for p in range(P)]
         dp1c, dac = [new(nl, H) for _ in range(P)], [new(nl, E) for _ in range(P)]
-        if GROUPED_PROJECTIONS:
+        if GROUPED_PROJECTIONS and plan.grouped_shapes:
             rel = plan.rel_of_path
             has = [p for p in range(P) if ranges[p][1] > ranges[p][0]]
             dslot = lambda p: dt2[ranges[p][0]:ranges[p][1], plan.slot[p] * D:(plan.slot[p] + 1) * D]
