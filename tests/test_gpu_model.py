@@ -368,3 +368,41 @@ def test_demand_driven_loss_equals_full_propagation(kind, entity_aware, shape):
     again = model.loss(batch)
     again.backward()
     assert again.item() == lean.item()
+
+
+def test_three_step_gat_channel_on_the_rows_its_batch_reads():
+    """A 3-step PEAGAT channel (the reference's tables are all 2-step; ``meta_path_steps`` allows more): with the batch
+    rows given, every earlier step runs on the rows the later ones read (source ranges accumulate step by step,
+    PEABaseChannel._needed_rows) - the batch rows of the output and all gradients equal the full channel's."""
+    from graph_recsys_benchmark_b200 import functional as F_
+    from graph_recsys_benchmark_b200.models.families import PEAGATChannel
+    from helpers import random_edge_index
+    torch.manual_seed(11)
+    n = 600
+    # three relations over four "types": 0-99 -> 100-299 -> 300-449 -> 450-599
+    e1 = random_edge_index(n, 2500, 1, src_range=(0, 100), dst_range=(100, 300))
+    e2 = random_edge_index(n, 2500, 2, src_range=(100, 300), dst_range=(300, 450))
+    e3 = random_edge_index(n, 2500, 3, src_range=(300, 450), dst_range=(450, 600))
+    eil = [e.to(DEV) for e in (e1, e2, e3)]
+    ch = PEAGATChannel(num_steps=3, num_nodes=n, dropout=0., emb_dim=64, hidden_size=64, repr_dim=16, num_heads=1).to(DEV)
+    x = torch.randn(n, 64, device=DEV)
+    batch_rows = torch.randint(450, 600, (40,), device=DEV)
+    active = F_.active_rows(batch_rows, n)
+    mask = torch.zeros(n, dtype=torch.bool, device=DEV)
+    mask[batch_rows] = True
+    w = torch.randn(n, 16, device=DEV) * mask[:, None]
+
+    def run(act):
+        ch.zero_grad()
+        xs = x.clone().requires_grad_(True)
+        y = ch.forward_split(xs, eil, None, False, act)
+        (y * w).sum().backward()
+        return y.detach(), [xs.grad.clone()] + [p.grad.clone() for p in ch.parameters()]
+    y0, g0 = run(None)
+    y1, g1 = run(active)
+    needed = ch._needed_rows(eil, n, active)
+    assert needed[0].ranges == [(100, 450)] and needed[1].ranges == [(300, 450)] and needed[2] is None
+    assert rel_err(y1[mask], y0[mask]) < 2e-6 and float(y1[~mask].abs().max()) == 0.
+    for a, b in zip(g1, g0):
+        if float(b.abs().max()) > 1e-12:
+            assert rel_err(a, b) < 5e-5

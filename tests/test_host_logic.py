@@ -330,3 +330,25 @@ def test_device_sampler_has_no_cpu_path():
     smp = DeviceBprSampler(SyntheticHIN('tiny', seed=7), 'cpu', seed=5)
     with pytest.raises(RuntimeError):
         smp.rows(torch.arange(4), epoch=0)
+
+
+def test_row_sets_count_every_row_once():
+    """functional.merge_ranges / RowSets (host logic of the demand-driven steps): ranges are joined when they overlap or
+    touch, and ``keep`` marks exactly one list entry per node that no range covers."""
+    from graph_recsys_benchmark_b200 import functional as F_
+    assert F_.merge_ranges([(40, 170), (150, 260), (500, 500), (610, 640), (260, 300)]) == [(40, 300), (610, 640)]
+    assert F_.merge_ranges([]) == [] and F_.merge_ranges([(7, 3)]) == []
+    ids = torch.tensor([3, 3, 41, 41, 41, 299, 300, 300, 611, 700, 700])           # sorted, duplicates kept
+    first = torch.ones_like(ids, dtype=torch.bool)
+    first[1:] = ids[1:] != ids[:-1]
+    active = F_.ActiveRows(torch.zeros(4, dtype=torch.int32), ids, first)
+    sets = F_.RowSets([(40, 170), (150, 300), (610, 640)], active)
+    keep = sets.keep()
+    assert keep.tolist() == [True, False, False, False, False, False, True, False, False, True, False]
+    assert sets.keep() is keep                                                     # cached per (ranges, step)
+    covered = set()
+    for lo, hi in sets.ranges:
+        covered |= set(range(lo, hi))
+    counted = sorted(covered | set(ids[keep].tolist()))
+    assert counted == sorted(covered | set(ids.tolist())) and len(ids[keep].tolist()) == len(set(ids[keep].tolist()))
+    assert sets.n_rows() == (300 - 40) + (640 - 610) + ids.numel()
