@@ -60,6 +60,22 @@ def test_csr_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.CsrView) == 8 * 2 + 4 * 4 + 8 * 2 + 8 + 8 * 3 + 8 + 8 + 8 + 8 * 2
 
 
+def test_group_problem_structs_match_header():
+    """The problem tables of the grouped launches (peagnn_linear_problem_t / peagnn_wgrad_problem_t): field order and
+    sizes of the ctypes mirrors follow the header's typedefs."""
+    from graph_recsys_benchmark_b200 import _lib
+    src = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
+    for typedef, mirror in (('peagnn_linear_problem_t', _lib.LinearProblem), ('peagnn_wgrad_problem_t', _lib.WgradProblem)):
+        body = re.search(r'typedef struct \{([^{}]*)\} %s;' % typedef, src).group(1)
+        fields = [re.split(r'[\s\*]+', d.strip())[-1] for d in body.split(';') if d.strip()]
+        assert fields == [name for name, _ in mirror._fields_], typedef
+        assert ctypes.sizeof(mirror) == 8 * len(fields)              # pointers and int64 only: no padding on LP64
+    assert int(re.search(r'#define PEAGNN_MAX_GROUP (\d+)', src).group(1)) == _lib.MAX_GROUP
+    # both tables travel by value in the kernel parameters: they have to stay below the 4 KB parameter space
+    assert 4 + 4 * (_lib.MAX_GROUP + 1) + _lib.MAX_GROUP * ctypes.sizeof(_lib.LinearProblem) < 4096
+    assert 8 + 4 * (_lib.MAX_GROUP + 1) + _lib.MAX_GROUP * (16 + ctypes.sizeof(_lib.WgradProblem)) < 4096
+
+
 def test_argument_errors_are_reported_not_crashed(lib):
     from graph_recsys_benchmark_b200 import _lib
     v = _lib.CsrView()
