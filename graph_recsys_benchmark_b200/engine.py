@@ -30,6 +30,8 @@ PARALLEL_BRANCHES = True      # False: _Fork runs its branches in order on the c
 GROUPED_PROJECTIONS = __import__('os').environ.get('PEAGNN_GROUPED', '1') != '0'   # demand-driven PEAGCN step: one launch per
                                                                                    # projection shape across the metapaths
 
+SAGE_LEAN = __import__('os').environ.get('PEAGNN_SAGE_LEAN', '1') != '0'    # demand-driven PEASage step: range / list projection passes
+
 N_BRANCHES = int(__import__('os').environ.get('PEAGNN_BRANCHES', '4'))     # side streams per device
 
 
@@ -813,12 +815,165 @@ class _SageBody(torch.autograd.Function):
         return (None, d_att, None, None, None, None, dx) + tuple(dM1) + tuple(grads)
 
 
+class _SageBodyLean(torch.autograd.Function):
+    """_SageBody for a demand-driven loss() (the PEASage counterpart of _GcnBodyLean).  SAGEConv has no self loops, so the
+    last step's mean aggregation on the batch rows reads T2 only on the node-id range of its relation's sources (the RANGE
+    pass), and the root term ``H1 Wroot2^T`` is wanted on the batch rows themselves (the LIST pass, on gathered [3B, .]
+    rows).  A row that is in the range and on the list has its first layer computed twice with the same result; its two
+    uses (T2 / root term) are different terms of Z, so both passes' gradients count.  Grouped launches (one per shape and
+    pass), the range chain and the list chain on parallel branches; fixed accumulation order: bit-reproducible."""
+
+    @staticmethod
+    def forward(ctx, plan, att, mode, n_rel, active, x, *tensors):
+        x = F_._rows(x)
+        M1 = [F_._rows(t) for t in tensors[:n_rel]]
+        params = [t.contiguous() for t in tensors[n_rel:]]
+        P, D, H, E = plan.P, plan.repr, plan.hidden, plan.emb
+        par = [params[6 * p:6 * p + 6] for p in range(P)]      # Wrel1, brel1, Wroot1, Wrel2, brel2, Wroot2
+        dev, n, wide = x.device, x.shape[0], P * D
+        ranges, rel = plan.source_ranges(), plan.rel_of_path
+        ids, nl = active.ids, int(active.ids.numel())
+        has = [p for p in range(P) if ranges[p][1] > ranges[p][0]]
+        new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        rng = lambda t, p: t[ranges[p][0]:ranges[p][1]]
+        slot = lambda t, p: t[:, plan.slot[p] * D:(plan.slot[p] + 1) * D]
+        m1c = [M1[r].index_select(0, ids) for r in range(n_rel)]
+        xc = x.index_select(0, ids)
+        h1r = [new(max(ranges[p][1] - ranges[p][0], 0), H) for p in range(P)]
+        h1c = [new(nl, H) for _ in range(P)]
+        t2, zroot = new(n, wide), new(nl, wide)
+        with _Fork(dev) as fork:
+            with fork.on(0):                                   # range: H1 = relu(M1 Wrel1^T + brel1 + x Wroot1^T), T2 = H1 Wrel2^T
+                F_.linear_grouped_raw([(rng(M1[rel[p]], p), par[p][0], par[p][1], h1r[p], None) for p in has], E, H, True)
+                F_.linear_grouped_raw([(rng(x, p), par[p][2], None, h1r[p], None) for p in has], E, H, True, relu=True,
+                                      accumulate=True)
+                F_.linear_grouped_raw([(h1r[p], par[p][3], None, slot(rng(t2, p), p), None) for p in has], H, D, True)
+            with fork.on(1):                                   # list: the same first layer, then the root term H1 Wroot2^T
+                F_.linear_grouped_raw([(m1c[rel[p]], par[p][0], par[p][1], h1c[p], None) for p in range(P)], E, H, True)
+                F_.linear_grouped_raw([(xc, par[p][2], None, h1c[p], None) for p in range(P)], E, H, True, relu=True,
+                                      accumulate=True)
+                F_.linear_grouped_raw([(h1c[p], par[p][5], None, slot(zroot, p), None) for p in range(P)], H, D, True)
+        z = new(n, wide)                                       # only the batch rows are written, and only they are read
+        plan.last_forward(t2, z, torch.cat([par[p][4] for p in plan.order]), active)
+        del t2
+        z_c = z.index_select(0, ids)
+        z_c.add_(zroot)
+        att_perm = att.reshape(P, D).index_select(0, plan.order_t).contiguous() if att is not None else None
+        out_c = new(nl, D)
+        with F_._on(dev):
+            F_._lib.call('peagnn_fuse_forward', F_._ptr(z_c), wide, nl, P, D, F_._ptr(att_perm), mode, -1,
+                         F_._ptr(out_c), D, F_._stream())
+        out = torch.zeros(n, D, dtype=torch.float32, device=dev)
+        out.index_copy_(0, ids, out_c)                         # duplicates rewrite the same row
+        ctx.plan, ctx.mode, ctx.n_rel, ctx.active, ctx.n_nodes = plan, mode, n_rel, active, n
+        ctx.att_shape = att.shape if att is not None else None
+        ctx.save_for_backward(z_c, att_perm, x, xc, *M1, *m1c, *h1r, *h1c,
+                              *[w for p in range(P) for w in (par[p][0], par[p][2], par[p][3], par[p][5])])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        plan, n_rel, active = ctx.plan, ctx.n_rel, ctx.active
+        P, D, H, E = plan.P, plan.repr, plan.hidden, plan.emb
+        saved = list(ctx.saved_tensors)
+        z_c, att_perm, x, xc = saved[:4]
+        pos = 4
+        M1 = saved[pos:pos + n_rel]; pos += n_rel
+        m1c = saved[pos:pos + n_rel]; pos += n_rel
+        h1r = saved[pos:pos + P]; pos += P
+        h1c = saved[pos:pos + P]; pos += P
+        ws = saved[pos:]
+        wrel1, wroot1 = [ws[4 * p] for p in range(P)], [ws[4 * p + 1] for p in range(P)]
+        wrel2, wroot2 = [ws[4 * p + 2] for p in range(P)], [ws[4 * p + 3] for p in range(P)]
+        dev, n, wide = z_c.device, ctx.n_nodes, P * D
+        ranges, rel = plan.source_ranges(), plan.rel_of_path
+        ids, first = active.ids, active.first
+        nl = int(ids.numel())
+        has = [p for p in range(P) if ranges[p][1] > ranges[p][0]]
+        new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        rng = lambda t, p: t[ranges[p][0]:ranges[p][1]]
+        slot = lambda t, p: t[:, plan.slot[p] * D:(plan.slot[p] + 1) * D]
+        # each node's gradient enters once, at its first occurrence on the list
+        dout_c = dout.index_select(0, ids) * first[:, None].to(torch.float32)
+        dz_c = new(nl, wide)
+        d_att_perm = new(P, D) if ctx.mode == 0 else None
+        need = int(F_._lib.query('peagnn_fuse_workspace_floats', nl, P, D)) if ctx.mode == 0 else 0
+        wsp = F_._ws(need, dev) if ctx.mode == 0 else None
+        with F_._on(dev):
+            F_._lib.call('peagnn_fuse_backward', F_._ptr(z_c), wide, nl, P, D, F_._ptr(att_perm), ctx.mode, F_._ptr(dout_c),
+                         dout_c.stride(0), F_._ptr(dz_c), wide, F_._ptr(d_att_perm), F_._ptr(wsp), need, F_._stream())
+        db2_all = new(wide)
+        F_.wgrad_raw(None, dz_c, 0, wide, 0, None, db2_all)                   # every metapath's d brel2 at once
+        dz = torch.zeros(n, wide, dtype=torch.float32, device=dev)
+        dz.index_add_(0, ids, dz_c)                            # later occurrences add exact zeros: order-independent
+        dt2 = plan.last_backward(dz, active)
+        dM1 = [torch.zeros(n, E, dtype=torch.float32, device=dev) for _ in range(n_rel)]
+        dx = torch.zeros(n, E, dtype=torch.float32, device=dev)
+        # range-pass (a) and list-pass (b) parts of every parameter gradient, summed at the end
+        dwrel1a, dbrel1a, dwroot1a = [new(H, E) for _ in range(P)], [new(H) for _ in range(P)], [new(H, E) for _ in range(P)]
+        dwrel1b, dbrel1b, dwroot1b = [new(H, E) for _ in range(P)], [new(H) for _ in range(P)], [new(H, E) for _ in range(P)]
+        dwrel2, dwroot2 = [new(D, H) for _ in range(P)], [new(D, H) for _ in range(P)]
+        dp1r = [new(max(ranges[p][1] - ranges[p][0], 0), H) for p in range(P)]
+        dp1c, dm1c, dxc = [new(nl, H) for _ in range(P)], [new(nl, E) for _ in range(P)], [new(nl, E) for _ in range(P)]
+
+        def rounds_by(key):
+            """has-metapaths that accumulate into one buffer region (same key) go into successive launches."""
+            out, seen = [], {}
+            for p in has:
+                k = seen.get(key(p), 0)
+                seen[key(p)] = k + 1
+                while len(out) <= k:
+                    out.append([])
+                out[k].append(p)
+            return out
+        with _Fork(dev) as fork:
+            with fork.on(0):                                   # range: d P1 = (d T2 Wrel2) gated by relu -> d M1, d x
+                F_.linear_grouped_raw([(slot(rng(dt2, p), p), wrel2[p], None, dp1r[p], h1r[p]) for p in has], D, H, False)
+                have_dp1r = fork.record()
+                for members in rounds_by(lambda p: rel[p]):
+                    F_.linear_grouped_raw([(dp1r[p], wrel1[p], None, rng(dM1[rel[p]], p), None) for p in members], H, E, False,
+                                          accumulate=True)
+                for members in rounds_by(lambda p: ranges[p]):
+                    F_.linear_grouped_raw([(dp1r[p], wroot1[p], None, rng(dx, p), None) for p in members], H, E, False,
+                                          accumulate=True)
+            with fork.on(1):                                   # range: weight gradients
+                F_.wgrad_grouped_raw([(h1r[p], slot(rng(dt2, p), p), dwrel2[p], None) for p in range(P)], H, D, True)
+                fork.wait(have_dp1r)
+                F_.wgrad_grouped_raw([(rng(M1[rel[p]], p), dp1r[p], dwrel1a[p], dbrel1a[p]) for p in range(P)], E, H, True)
+                F_.wgrad_grouped_raw([(rng(x, p), dp1r[p], dwroot1a[p], None) for p in range(P)], E, H, True)
+            with fork.on(2):                                   # list: d P1 = (d Z Wroot2) gated by relu -> d M1, d x rows
+                F_.linear_grouped_raw([(slot(dz_c, p), wroot2[p], None, dp1c[p], h1c[p]) for p in range(P)], D, H, False)
+                have_dp1c = fork.record()
+                F_.linear_grouped_raw([(dp1c[p], wrel1[p], None, dm1c[p], None) for p in range(P)], H, E, False)
+                F_.linear_grouped_raw([(dp1c[p], wroot1[p], None, dxc[p], None) for p in range(P)], H, E, False)
+            with fork.on(3):                                   # list: weight gradients
+                F_.wgrad_grouped_raw([(h1c[p], slot(dz_c, p), dwroot2[p], None) for p in range(P)], H, D, True)
+                fork.wait(have_dp1c)
+                F_.wgrad_grouped_raw([(m1c[rel[p]], dp1c[p], dwrel1b[p], dbrel1b[p]) for p in range(P)], E, H, True)
+                F_.wgrad_grouped_raw([(xc, dp1c[p], dwroot1b[p], None) for p in range(P)], E, H, True)
+        for p in range(P):                                     # non-first list entries carry exact zeros: order-independent
+            dM1[rel[p]].index_add_(0, ids, dm1c[p])
+            dx.index_add_(0, ids, dxc[p])
+        torch._foreach_add_(dwrel1a + dbrel1a + dwroot1a, dwrel1b + dbrel1b + dwroot1b)
+        grads = []
+        for p in range(P):
+            s = plan.slot[p]
+            grads.extend([dwrel1a[p], dbrel1a[p], dwroot1a[p], dwrel2[p], db2_all[s * D:(s + 1) * D], dwroot2[p]])
+        d_att = None
+        if d_att_perm is not None:
+            d_att = torch.empty_like(d_att_perm)
+            d_att.index_copy_(0, plan.order_t, d_att_perm)
+            d_att = d_att.reshape(ctx.att_shape)
+        return (None, d_att, None, None, None, dx) + tuple(dM1) + tuple(grads)
+
+
 def sage_forward(model, metapath_idx=None, active=None):
     """model.forward() of a standard PEASage model through the fused engine."""
     plan = getattr(model, '_sage_plan', None)
     if plan is None:
         plan = model._sage_plan = GcnPlan(model, 'sage')
-    m1 = _GcnHead.apply(model.x, plan)
+    lean = (SAGE_LEAN and active is not None and active.ids is not None and metapath_idx is None and plan.grouped_shapes)
+    m1 = _GcnHead.apply(model.x, plan, plan.head_row_bitmaps(active) if lean else None)
     params = []
     for ch in model.pea_channels:
         l0, l1 = ch.gnn_layers
@@ -826,5 +981,7 @@ def sage_forward(model, metapath_idx=None, active=None):
                        l1.lin_rel.weight, l1.lin_rel.bias, l1.lin_root.weight])
     att = model.att if model.channel_aggr == 'att' else None
     mode = 0 if model.channel_aggr == 'att' else 1
+    if lean:
+        return _SageBodyLean.apply(plan, att, mode, len(m1), active, model.x, *m1, *params)
     skip = -1 if metapath_idx is None else int(metapath_idx)
     return _SageBody.apply(plan, att, mode, skip, len(m1), active, model.x, *m1, *params)
